@@ -1,0 +1,178 @@
+/* singlet_cuda.h -- C ABI of libsinglet_cuda.so: the B200 (sm_100a) ALS-NMF engine that replaces the
+ * C++ core of zdebruine/singlet behind its Rcpp entry points.
+ *
+ * Every function returns 0 on success or a negative SGL_E* code; the message is available from
+ * sgl_last_error() (thread-local). No C++ exception and no longjmp ever crosses this boundary
+ * (the reference relies on BEGIN_RCPP/END_RCPP, src/RcppExports.cpp:18,26). There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with SGL_ENODEVICE.
+ *
+ * Matrix conventions are the reference's: factors are column-major k x cols doubles
+ * (w is k x m, h is k x n, element (f, c) at c*k + f); sparse inputs are dgCMatrix slot views
+ * (inst/include/singlet.h:36-41) given as a list of column chunks (n_chunks = 1 for one matrix).
+ *
+ * Two layers:
+ *   (1) host-facing entry points -- what src/RcppExports.cpp binds, one per reference routine;
+ *   (2) device-level building blocks (sgl_dev_*) on caller-owned device buffers and the handle's
+ *       stream -- used by the one-process-per-GPU driver (singlet_b200/sharded.py) which supplies
+ *       the NCCL collectives between them, and by the parity tests.
+ */
+#ifndef SINGLET_CUDA_H
+#define SINGLET_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGL_OK 0
+#define SGL_EINVAL (-1)      /* bad argument (shape, NULL, k out of range ...) */
+#define SGL_ENODEVICE (-2)   /* no CUDA device / wrong architecture */
+#define SGL_ECUDA (-3)       /* CUDA runtime error (message in sgl_last_error) */
+#define SGL_EINTERRUPT (-4)  /* poll_interrupt callback asked to stop */
+#define SGL_ENOMEM (-5)
+
+#define SGL_MAX_RANK 128
+
+/* dgCMatrix view: replaces Rcpp::SparseMatrix (inst/include/singlet.h:36-41). Read-only, caller
+ * owned, must stay valid for the duration of the call only. */
+typedef struct sgl_csc {
+    int64_t nrow, ncol;
+    const int32_t* p; /* ncol + 1 */
+    const int32_t* i; /* nnz, 0-based rows, ascending within a column */
+    const double* x;  /* nnz */
+} sgl_csc;
+
+/* Replaces Rprintf / Rcpp::checkUserInterrupt (src/singlet.cpp:643-663, 1102-1128). Both callbacks
+ * are invoked on the calling thread only, between half-iterations. Either may be NULL. */
+typedef struct sgl_callbacks {
+    void* user;
+    int (*poll_interrupt)(void* user);                                  /* non-zero -> abort fit */
+    void (*on_iter)(void* user, int iter, double tol, double overfit);  /* overfit = NaN if untraced */
+} sgl_callbacks;
+
+/* CV trace vectors of c_ard_nmf (src/singlet.cpp:1144-1151). Caller allocates `capacity` entries
+ * (maxit + 2 is always enough); the library sets `length`. */
+typedef struct sgl_trace {
+    double* test_mse;
+    int32_t* iter;
+    double* tol;
+    double* score_overfit;
+    int32_t capacity;
+    int32_t length;
+} sgl_trace;
+
+typedef struct sgl_handle sgl_handle; /* one device + one stream + cached device matrices */
+typedef struct sgl_matrix sgl_matrix; /* device-resident sparse matrix in the engine's tiled layout */
+
+/* ---- library / handle ------------------------------------------------------------------- */
+int sgl_version(void);
+const char* sgl_last_error(void);
+int sgl_device_count(void);
+/* stream: a cudaStream_t to run on (e.g. torch's current stream) or NULL to create one. */
+int sgl_create(int device, void* stream, sgl_handle** out);
+int sgl_destroy(sgl_handle* h);
+/* Keep uploaded A/At (and the materialised mask) between calls when the same host buffers are
+ * passed again (a CV sweep makes dozens of calls on one matrix). Default on. */
+int sgl_set_cache(sgl_handle* h, int enabled);
+int sgl_synchronize(sgl_handle* h);
+/* kernel launches issued through this handle so far (bench.py's gpu_launches) */
+int64_t sgl_launch_count(sgl_handle* h);
+
+/* ---- host-facing entry points (one per reference routine) -------------------------------- */
+
+/* c_nmf / c_nmf_sparse_list: src/singlet.cpp:638-672, 715-743 (RcppExports.cpp:97-116, 138-155).
+ * w: k x m in (w_init) / out; d: k out; h: k x n out. iters_out / tol_out may be NULL. */
+int sgl_nmf(sgl_handle* h, const sgl_csc* A, int nA, const sgl_csc* At, int nAt, double tol, uint16_t maxit,
+            double L1_w, double L1_h, double L2_w, double L2_h, int k, double* w, double* d, double* h_out,
+            int32_t* iters_out, double* tol_out, const sgl_callbacks* cb);
+
+/* c_ard_nmf / c_ard_nmf_sparse_list: src/singlet.cpp:1090-1234 (RcppExports.cpp:283-327). */
+int sgl_ard_nmf(sgl_handle* h, const sgl_csc* A, int nA, const sgl_csc* At, int nAt, double tol, uint16_t maxit,
+                double L1, double L2, int k, double* w, double* d, double* h_out, uint64_t seed,
+                uint64_t inv_density, double overfit_threshold, uint16_t trace_test_mse, sgl_trace* trace,
+                const sgl_callbacks* cb);
+
+/* c_project_model: src/singlet.cpp:405-413 (RcppExports.cpp:82-95). w is w_rows x w_cols column-major;
+ * it is transposed when w_rows == nrow(A) exactly as the reference does. h: k x n out, d: k out. */
+int sgl_project_model(sgl_handle* h, const sgl_csc* A, int nA, const double* w, int64_t w_rows, int64_t w_cols,
+                      double L1, double L2, double* h_out, double* d_out);
+
+/* Rcpp_predict: src/singlet.cpp:350-367 (RcppExports.cpp:67-80): one H update from h = 0, no scaling. */
+int sgl_predict(sgl_handle* h, const sgl_csc* A, int nA, const double* w, int64_t w_rows, int64_t w_cols, double L1,
+                double L2, double* h_out);
+
+/* ---- test hooks for the bit-exact parts ----------------------------------------------------
+ * rng::rand(i,j) / rng::draw (src/singlet.cpp:47-64, 91-95) evaluated ON THE DEVICE for n pairs. */
+int sgl_mask_rand(sgl_handle* h, uint64_t seed, const uint64_t* i, const uint64_t* j, int64_t n, uint64_t* out);
+int sgl_mask_draw(sgl_handle* h, uint64_t seed, uint64_t inv_density, const uint64_t* i, const uint64_t* j,
+                  int64_t n, uint8_t* out);
+
+/* ---- device-level building blocks ---------------------------------------------------------
+ * Factor buffers are float [cols][KP] (KP = sgl_padded_rank(k): k rounded up to 4,8,16,32,64,128;
+ * padding lanes hold 0). Scalars that are reduced across GPUs are double. All work is enqueued on
+ * the handle's stream; nothing synchronises unless stated. */
+int sgl_padded_rank(int k);
+
+/* Upload a chunk list (concatenated by columns) and build the gather-tile index. */
+int sgl_matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl_matrix** out);
+/* Deterministic synthetic sparse counts (exact rules in singlet_b200/synth.py),
+ * generated on the device. Orientation 0: columns = cells [col0, col0+ncol) of the m x n matrix;
+ * orientation 1: columns = genes [col0, col0+ncol) of its transpose. values_table: 8 floats. */
+int sgl_matrix_synth(sgl_handle* h, int64_t m_genes, int64_t n_cells, double density, uint64_t data_seed,
+                     int orientation, int64_t col0, int64_t ncol, const float* values_table, sgl_matrix** out);
+int sgl_matrix_free(sgl_handle* h, sgl_matrix* m);
+int sgl_matrix_info(const sgl_matrix* m, int64_t* nrow, int64_t* ncol, int64_t* nnz);
+/* Copy back to host in dgCMatrix form (p may be int32 only if nnz < 2^31). Synchronises. */
+int sgl_matrix_download(sgl_handle* h, const sgl_matrix* m, int32_t* p, int32_t* i, double* x);
+
+/* double k x cols (column-major, host) <-> float [cols][KP] (device) */
+int sgl_factor_upload(sgl_handle* h, const double* host_kxc, int k, int64_t cols, float* dev);
+int sgl_factor_download(sgl_handle* h, const float* dev, int k, int64_t cols, double* host_kxc);
+
+/* AAt (src/singlet.cpp:200-206) partial: gram[KP*KP] (double, device) = sum over the given columns
+ * of f f^T. add_jitter != 0 adds the 1e-15 diagonal (do it once, after any all-reduce). */
+int sgl_dev_gram(sgl_handle* h, const float* F, int k, int64_t cols, double* gram, int add_jitter);
+int sgl_dev_gram_jitter(sgl_handle* h, int k, double* gram);
+
+/* predict (src/singlet.cpp:333-347) for the columns of X: b = F_in . X[:, c] then coordinate-descent
+ * NNLS against `gram` (double [KP*KP], jitter included) with warm start / result in F_out; empty
+ * columns are skipped. rowsum[KP] (double, device) receives the row sums of the new F_out
+ * (the local part of `scale`'s d, without the 1e-15). */
+int sgl_dev_update(sgl_handle* h, const sgl_matrix* X, const float* F_in, float* F_out, int k, const double* gram,
+                   double L1, double L2, double* rowsum);
+
+/* scale (src/singlet.cpp:219-225): F[c][f] /= d[f]; d is double[KP] on the device (already
+ * all-reduced and with the 1e-15 added -- see sgl_dev_finish_d). */
+int sgl_dev_finish_d(sgl_handle* h, int k, double* d_inout);
+int sgl_dev_scale(sgl_handle* h, float* F, int k, int64_t cols, const double* d);
+
+/* cor (src/singlet.cpp:184-197): the five running sums over the given columns -> sums[5] (double,
+ * device): sum x, sum y, sum xy, sum x^2, sum y^2. sgl_cor_from_sums finishes on the host. */
+int sgl_dev_cor_sums(sgl_handle* h, const float* X, const float* Y, int k, int64_t cols, double* sums);
+double sgl_cor_from_sums(const double* sums5, double n_elems);
+
+/* Speckled mask (src/singlet.cpp:436-466, 536-568), materialised once per (seed, inv_density):
+ * a training copy of X with held-out non-zeros zeroed plus the per-column held-out index lists.
+ * mask_t = 0: columns are cells (hash(col+col_offset, row+row_offset)); 1: columns are genes. */
+typedef struct sgl_mask sgl_mask;
+int sgl_mask_build(sgl_handle* h, const sgl_matrix* X, uint64_t seed, uint64_t inv_density, int mask_t,
+                   int64_t col_offset, int64_t row_offset, sgl_mask** out);
+int sgl_mask_free(sgl_handle* h, sgl_mask* m);
+int sgl_mask_info(const sgl_mask* m, int64_t* n_masked, int64_t* n_masked_nonzero);
+/* held-out row indices of one column (host copy; for bit-exactness tests). Returns count. */
+int64_t sgl_mask_column(sgl_handle* h, const sgl_mask* m, int64_t col, int32_t* rows_out, int64_t capacity);
+
+/* predict_mask (src/singlet.cpp:436-466) */
+int sgl_dev_update_masked(sgl_handle* h, const sgl_matrix* X, const sgl_mask* mask, const float* F_in, float* F_out,
+                          int k, const double* gram, double L1, double L2, double* rowsum);
+/* mse_test (src/singlet.cpp:536-568) over the cell columns of `mask` (mask_t = 0): writes the SUM of
+ * per-column losses to loss_sum[0] (double, device); divide by the global n afterwards.
+ * which = 0: held-out entries (test); 1: the entries that are not held out (train, harness-defined). */
+int sgl_dev_mse(sgl_handle* h, const sgl_matrix* A, const sgl_mask* mask, const float* W, const double* d,
+                const float* H, int k, int which, double* loss_sum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SINGLET_CUDA_H */

@@ -1,0 +1,1173 @@
+// engine.cu -- host side of libsinglet_cuda.so: device objects, kernel launchers, the ALS drivers
+// that restate c_nmf_base / c_ard_nmf_base / c_project_model (reference src/singlet.cpp:638-666,
+// 1090-1152, 405-413) as stream-ordered kernel sequences, and the extern "C" surface declared in
+// include/singlet_cuda.h.  sm_100a only; no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "misc.cuh"
+#include "nnls.cuh"
+#include "spmm.cuh"
+
+namespace sgl {
+
+std::string& last_error() {
+    static thread_local std::string e;
+    return e;
+}
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+
+template <typename T>
+struct DevBuf {  // grow-only device scratch
+    T* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return SGL_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) return fail(SGL_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        cap = n;
+        return SGL_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct TileIndex {
+    int rb_rows = 0, n_tiles = 0;
+    int64_t ncol_pad = 0;
+    int32_t* tileptr = nullptr;
+};
+
+}  // namespace sgl
+
+using namespace sgl;
+
+struct sgl_matrix {
+    int64_t nrow = 0, ncol = 0, nnz = 0;
+    int64_t* colptr = nullptr;  // ncol + 1
+    uint2* rec = nullptr;       // nnz records {row, value bits}
+    std::map<int, TileIndex> tiles;  // per padded rank
+    uint64_t fingerprint = 0;        // host-buffer identity for the upload cache
+};
+
+struct sgl_mask {
+    const sgl_matrix* X = nullptr;
+    uint64_t seed = 0, inv_density = 0;
+    int mask_t = 0;
+    int64_t col_offset = 0, row_offset = 0;
+    uint2* rec_train = nullptr;  // copy of X->rec with held-out values zeroed
+    int64_t* mptr = nullptr;     // ncol + 1
+    uint2* mrec = nullptr;       // held-out {row, value bits}
+    int64_t n_masked = 0, n_masked_nz = 0;
+};
+
+struct sgl_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int64_t launches = 0;
+    bool cache = true;
+    DevBuf<float> bparts, gram_f, gram_f_nojit, inv_diag;
+    DevBuf<double> part, scal, losses, gram_w;
+    DevBuf<int64_t> counts;
+    double* pinned = nullptr;  // 64 doubles of pinned host scratch
+    // upload cache (host-facing entry points)
+    sgl_matrix* cA = nullptr;
+    sgl_matrix* cAt = nullptr;
+    sgl_mask* cmA = nullptr;
+    sgl_mask* cmAt = nullptr;
+};
+
+namespace sgl {
+
+#define LAUNCH_CHECK(h)                                                                             \
+    do {                                                                                            \
+        ++(h)->launches;                                                                            \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess) return fail(SGL_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+#define DISPATCH_KP(KPV, ...)                          \
+    switch (KPV) {                                     \
+        case 4: { constexpr int KP = 4; __VA_ARGS__; } break;     \
+        case 8: { constexpr int KP = 8; __VA_ARGS__; } break;     \
+        case 16: { constexpr int KP = 16; __VA_ARGS__; } break;   \
+        case 32: { constexpr int KP = 32; __VA_ARGS__; } break;   \
+        case 64: { constexpr int KP = 64; __VA_ARGS__; } break;   \
+        case 128: { constexpr int KP = 128; __VA_ARGS__; } break; \
+        default: return fail(SGL_EINVAL, "unsupported padded rank %d", KPV); \
+    }
+
+static int check_k(int k) {
+    if (k < 1 || k > SGL_MAX_RANK) return fail(SGL_EINVAL, "rank k=%d outside [1, %d]", k, SGL_MAX_RANK);
+    return SGL_OK;
+}
+
+static int set_device(sgl_handle* h) {
+    SGL_CUDA(cudaSetDevice(h->device));
+    return SGL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// matrices
+// ---------------------------------------------------------------------------------------------
+static void matrix_release(sgl_matrix* m) {
+    if (!m) return;
+    if (m->colptr) cudaFree(m->colptr);
+    if (m->rec) cudaFree(m->rec);
+    for (auto& kv : m->tiles)
+        if (kv.second.tileptr) cudaFree(kv.second.tileptr);
+    delete m;
+}
+static void mask_release(sgl_mask* m) {
+    if (!m) return;
+    if (m->rec_train) cudaFree(m->rec_train);
+    if (m->mptr) cudaFree(m->mptr);
+    if (m->mrec) cudaFree(m->mrec);
+    delete m;
+}
+
+static uint64_t fingerprint_chunks(const sgl_csc* c, int n) {
+    uint64_t f = 0x243F6A8885A308D3ull;
+    auto mix = [&](uint64_t v) { f = splitmix64(f ^ v); };
+    for (int q = 0; q < n; ++q) {
+        mix((uint64_t)(uintptr_t)c[q].p);
+        mix((uint64_t)(uintptr_t)c[q].i);
+        mix((uint64_t)(uintptr_t)c[q].x);
+        mix((uint64_t)c[q].nrow);
+        mix((uint64_t)c[q].ncol);
+        const int64_t nnz = c[q].p[c[q].ncol];
+        mix((uint64_t)nnz);
+        // sample of the contents so that in-place edits of the host buffers are noticed
+        const int64_t step = nnz > 4096 ? nnz / 4096 : 1;
+        for (int64_t t = 0; t < nnz; t += step) {
+            uint64_t bits;
+            std::memcpy(&bits, &c[q].x[t], 8);
+            mix(bits ^ ((uint64_t)(uint32_t)c[q].i[t] << 1));
+        }
+        const int64_t cstep = c[q].ncol > 1024 ? c[q].ncol / 1024 : 1;
+        for (int64_t t = 0; t <= c[q].ncol; t += cstep) mix((uint64_t)c[q].p[t]);
+    }
+    return f;
+}
+
+static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl_matrix** out) {
+    if (!chunks || n_chunks < 1) return fail(SGL_EINVAL, "matrix upload: empty chunk list");
+    int64_t nrow = chunks[0].nrow, ncol = 0, nnz = 0;
+    for (int q = 0; q < n_chunks; ++q) {
+        const sgl_csc& c = chunks[q];
+        if (!c.p || (c.p[c.ncol] > 0 && (!c.i || !c.x))) return fail(SGL_EINVAL, "matrix upload: NULL slot in chunk %d", q);
+        if (c.nrow != nrow) return fail(SGL_EINVAL, "matrix upload: chunk %d has %lld rows, expected %lld", q, (long long)c.nrow, (long long)nrow);
+        if (c.nrow < 1 || c.nrow > 0x7fffffffLL || c.ncol < 0) return fail(SGL_EINVAL, "matrix upload: bad dimensions in chunk %d", q);
+        if (c.p[0] != 0) return fail(SGL_EINVAL, "matrix upload: p[0] != 0 in chunk %d", q);
+        for (int64_t t = 0; t < c.ncol; ++t)
+            if (c.p[t + 1] < c.p[t]) return fail(SGL_EINVAL, "matrix upload: p not monotone in chunk %d", q);
+        ncol += c.ncol;
+        nnz += c.p[c.ncol];
+    }
+    SGL_TRY(set_device(h));
+    sgl_matrix* m = new sgl_matrix();
+    m->nrow = nrow;
+    m->ncol = ncol;
+    m->nnz = nnz;
+    cudaError_t e1 = cudaMalloc(&m->colptr, sizeof(int64_t) * (size_t)(ncol + 1));
+    cudaError_t e2 = cudaMalloc(&m->rec, sizeof(uint2) * (size_t)(nnz > 0 ? nnz : 1));
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        matrix_release(m);
+        return fail(SGL_ENOMEM, "matrix upload: cudaMalloc failed for %lld non-zeros", (long long)nnz);
+    }
+    // staging: pieces of at most PIECE non-zeros go through temporary device buffers
+    const int64_t PIECE = 32ll << 20;
+    int32_t* d_idx = nullptr;
+    double* d_val = nullptr;
+    int32_t* d_p = nullptr;
+    int64_t max_cols = 0;
+    for (int q = 0; q < n_chunks; ++q) max_cols = chunks[q].ncol > max_cols ? chunks[q].ncol : max_cols;
+    const int64_t piece = nnz < PIECE ? (nnz > 0 ? nnz : 1) : PIECE;
+    if (cudaMalloc(&d_idx, sizeof(int32_t) * piece) != cudaSuccess || cudaMalloc(&d_val, sizeof(double) * piece) != cudaSuccess ||
+        cudaMalloc(&d_p, sizeof(int32_t) * (size_t)(max_cols + 1)) != cudaSuccess) {
+        if (d_idx) cudaFree(d_idx);
+        if (d_val) cudaFree(d_val);
+        if (d_p) cudaFree(d_p);
+        matrix_release(m);
+        return fail(SGL_ENOMEM, "matrix upload: staging cudaMalloc failed");
+    }
+    int rc = SGL_OK;
+    int64_t col_off = 0, nnz_off = 0;
+    for (int q = 0; q < n_chunks && rc == SGL_OK; ++q) {
+        const sgl_csc& c = chunks[q];
+        const int64_t cn = c.p[c.ncol];
+        cudaMemcpyAsync(d_p, c.p, sizeof(int32_t) * (size_t)(c.ncol + 1), cudaMemcpyHostToDevice, h->stream);
+        const int last = (q == n_chunks - 1) ? 1 : 0;
+        colptr_from_p32_kernel<<<blocks_for(c.ncol + 1, 256), 256, 0, h->stream>>>(d_p, c.ncol, nnz_off, m->colptr + col_off, last);
+        ++h->launches;
+        for (int64_t o = 0; o < cn; o += piece) {
+            const int64_t len = (cn - o) < piece ? (cn - o) : piece;
+            cudaMemcpyAsync(d_idx, c.i + o, sizeof(int32_t) * (size_t)len, cudaMemcpyHostToDevice, h->stream);
+            cudaMemcpyAsync(d_val, c.x + o, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, h->stream);
+            pack_records_kernel<<<blocks_for(len, 256), 256, 0, h->stream>>>(d_idx, d_val, len, m->rec + nnz_off + o);
+            ++h->launches;
+        }
+        if (cudaGetLastError() != cudaSuccess) rc = fail(SGL_ECUDA, "matrix upload: copy/pack failed");
+        col_off += c.ncol;
+        nnz_off += cn;
+    }
+    if (ncol == 0) {
+        const int64_t zero = 0;
+        cudaMemcpyAsync(m->colptr, &zero, sizeof(int64_t), cudaMemcpyHostToDevice, h->stream);
+    }
+    cudaError_t es = cudaStreamSynchronize(h->stream);
+    cudaFree(d_idx);
+    cudaFree(d_val);
+    cudaFree(d_p);
+    if (rc == SGL_OK && es != cudaSuccess) rc = fail(SGL_ECUDA, "matrix upload: %s", cudaGetErrorString(es));
+    if (rc != SGL_OK) {
+        matrix_release(m);
+        return rc;
+    }
+    *out = m;
+    return SGL_OK;
+}
+
+// tile index for padded rank KP (lazily built, cached on the matrix)
+static int get_tiles(sgl_handle* h, sgl_matrix* m, int kpv, const TileIndex** out) {
+    auto it = m->tiles.find(kpv);
+    if (it != m->tiles.end()) {
+        *out = &it->second;
+        return SGL_OK;
+    }
+    TileIndex ti;
+    int rows = spmm_tile_rows(kpv);
+    // small problems: shrink the tile so that (column groups x tiles) can fill the chip
+    int cols_per_cta = 0;
+    DISPATCH_KP(kpv, cols_per_cta = SpmmCfg<KP>::COLS_PER_CTA);
+    const int64_t groups = (m->ncol + cols_per_cta - 1) / cols_per_cta;
+    if (groups < 2 * h->sm_count) {
+        const int64_t want_tiles = (2 * h->sm_count + groups - 1) / (groups > 0 ? groups : 1);
+        int64_t r = (m->nrow + want_tiles - 1) / want_tiles;
+        r = (r + 7) & ~7ll;
+        if (r < 128) r = 128;
+        if (r < rows) rows = (int)r;
+    }
+    ti.rb_rows = rows;
+    ti.n_tiles = (int)((m->nrow + rows - 1) / rows);
+    ti.ncol_pad = (m->ncol + 31) & ~31ll;
+    if (ti.ncol_pad == 0) ti.ncol_pad = 32;
+    SGL_CUDA(cudaMalloc(&ti.tileptr, sizeof(int32_t) * (size_t)ti.ncol_pad * (size_t)(ti.n_tiles + 1)));
+    dim3 grid(blocks_for(ti.ncol_pad, 256), (unsigned)(ti.n_tiles + 1));
+    build_tileptr_kernel<<<grid, 256, 0, h->stream>>>(m->rec, m->colptr, m->ncol, ti.ncol_pad, ti.rb_rows, ti.n_tiles, ti.tileptr);
+    LAUNCH_CHECK(h);
+    m->tiles[kpv] = ti;
+    *out = &m->tiles[kpv];
+    return SGL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers
+// ---------------------------------------------------------------------------------------------
+static int reduce_partials(sgl_handle* h, const double* part, int64_t n_parts, int width, double* out) {
+    reduce_partials_kernel<<<width, 256, 0, h->stream>>>(part, n_parts, width, out);
+    LAUNCH_CHECK(h);
+    return SGL_OK;
+}
+
+static int dev_gram(sgl_handle* h, const float* F, int k, int64_t cols, double* gram, bool jitter) {
+    const int KPV = kp_of(k);
+    int tile_cols = 128;
+    DISPATCH_KP(KPV, tile_cols = GramCfg<KP>::TILE_COLS);
+    int64_t grid = (cols + tile_cols - 1) / tile_cols;
+    if (grid > 2 * h->sm_count) grid = 2 * h->sm_count;
+    if (grid < 1) grid = 1;
+    SGL_TRY(h->part.ensure((size_t)grid * KPV * KPV));
+    DISPATCH_KP(KPV, (gram_partial_kernel<KP><<<(unsigned)grid, 256, 0, h->stream>>>(F, cols, h->part.p)));
+    LAUNCH_CHECK(h);
+    SGL_TRY(reduce_partials(h, h->part.p, grid, KPV * KPV, gram));
+    if (jitter) {
+        add_jitter_kernel<<<1, 128, 0, h->stream>>>(gram, k, KPV);
+        LAUNCH_CHECK(h);
+    }
+    return SGL_OK;
+}
+
+template <int KP>
+static int launch_spmm(sgl_handle* h, const sgl_matrix* X, const uint2* rec, const TileIndex& ti, const float* F,
+                       float* Bout, int splits, int tiles_per_split) {
+    using C = SpmmCfg<KP>;
+    const size_t smem = 2 * (size_t)ti.rb_rows * KP * sizeof(float) + 2 * sizeof(uint64_t);
+    static bool attr_done = false;
+    if (!attr_done) {
+        SGL_CUDA(cudaFuncSetAttribute(spmm_tiles_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    dim3 grid(blocks_for(X->ncol, C::COLS_PER_CTA), (unsigned)splits);
+    spmm_tiles_kernel<KP><<<grid, C::WARPS * 32, smem, h->stream>>>(rec, X->colptr, ti.tileptr, X->ncol, ti.ncol_pad, X->nrow,
+                                                                   ti.rb_rows, ti.n_tiles, tiles_per_split, F, Bout);
+    LAUNCH_CHECK(h);
+    return SGL_OK;
+}
+
+// predict / predict_mask for all columns of X (src/singlet.cpp:333-347, 436-466)
+static int dev_update(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask, const float* F_in, float* F_out, int k,
+                      const double* gram, double L1, double L2, double* rowsum) {
+    sgl_matrix* X = const_cast<sgl_matrix*>(Xc);
+    const int KPV = kp_of(k);
+    if (X->ncol == 0) {
+        SGL_CUDA(cudaMemsetAsync(rowsum, 0, sizeof(double) * KPV, h->stream));
+        return SGL_OK;
+    }
+    const TileIndex* ti = nullptr;
+    SGL_TRY(get_tiles(h, X, KPV, &ti));
+    SGL_TRY(h->gram_f.ensure((size_t)KPV * KPV));
+    SGL_TRY(h->gram_f_nojit.ensure((size_t)KPV * KPV));
+    SGL_TRY(h->inv_diag.ensure((size_t)KPV));
+    gram_finish_kernel<<<1, 256, 0, h->stream>>>(gram, k, KPV, h->gram_f.p, h->gram_f_nojit.p, h->inv_diag.p);
+    LAUNCH_CHECK(h);
+
+    // split the tile range when there are too few column groups to fill the chip
+    int cols_per_cta = 0;
+    DISPATCH_KP(KPV, cols_per_cta = SpmmCfg<KP>::COLS_PER_CTA);
+    const int64_t groups = (X->ncol + cols_per_cta - 1) / cols_per_cta;
+    int splits = 1;
+    if (groups < 2 * h->sm_count) {
+        splits = (int)((4 * h->sm_count + groups - 1) / groups);
+        if (splits > ti->n_tiles) splits = ti->n_tiles;
+        if (splits > 16) splits = 16;
+        if (splits < 1) splits = 1;
+    }
+    const int tiles_per_split = (ti->n_tiles + splits - 1) / splits;
+    splits = (ti->n_tiles + tiles_per_split - 1) / tiles_per_split;
+    SGL_TRY(h->bparts.ensure((size_t)splits * (size_t)X->ncol * KPV));
+    const uint2* rec = mask ? mask->rec_train : X->rec;
+    DISPATCH_KP(KPV, SGL_TRY(launch_spmm<KP>(h, X, rec, *ti, F_in, h->bparts.p, splits, tiles_per_split)));
+
+    int64_t n_parts = 0;
+    if (!mask) {
+        if (KPV <= 64) {
+            int nt = 128;
+            DISPATCH_KP(KPV, nt = NnlsCfg<(KP <= 64 ? KP : 64)>::THREADS);
+            n_parts = (X->ncol + nt - 1) / nt;
+            SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
+            switch (KPV) {
+#define NNLS_CASE(KPC)                                                                                              \
+    case KPC:                                                                                                       \
+        nnls_cols_kernel<KPC><<<(unsigned)n_parts, NnlsCfg<KPC>::THREADS, 0, h->stream>>>(                           \
+            h->bparts.p, splits, F_out, h->gram_f.p, h->inv_diag.p, X->colptr, X->ncol, k, (float)L1, (float)L2, h->part.p); \
+        break;
+                NNLS_CASE(4) NNLS_CASE(8) NNLS_CASE(16) NNLS_CASE(32) NNLS_CASE(64)
+                default: break;
+#undef NNLS_CASE
+            }
+        } else {
+            n_parts = (X->ncol + 31) / 32;
+            SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
+            const size_t smem = 2 * (size_t)KPV * 32 * sizeof(float);
+            nnls_cols_big_kernel<<<(unsigned)n_parts, 32, smem, h->stream>>>(h->bparts.p, splits, F_out, h->gram_f.p, h->inv_diag.p,
+                                                                            X->colptr, X->ncol, k, KPV, (float)L1, (float)L2, h->part.p);
+        }
+        LAUNCH_CHECK(h);
+    } else {
+        if (KPV <= 64) {
+            const int warps = 4;
+            n_parts = (X->ncol + warps - 1) / warps;
+            SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
+            switch (KPV) {
+#define MASKED_CASE(KPC)                                                                                            \
+    case KPC:                                                                                                       \
+        nnls_masked_kernel<KPC><<<(unsigned)n_parts, MaskedCfg<KPC>::WARPS * 32, 0, h->stream>>>(                    \
+            h->bparts.p, splits, F_out, h->gram_f_nojit.p, F_in, X->colptr, mask->mptr, mask->mrec, X->ncol, k, (float)L1, \
+            (float)L2, h->part.p);                                                                                  \
+        break;
+                MASKED_CASE(4) MASKED_CASE(8) MASKED_CASE(16) MASKED_CASE(32) MASKED_CASE(64)
+                default: break;
+#undef MASKED_CASE
+            }
+        } else {
+            n_parts = X->ncol;
+            SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
+            const size_t smem = ((size_t)KPV * (KPV + 1) + 3 * (size_t)KPV) * sizeof(float);
+            static bool attr_done = false;
+            if (!attr_done) {
+                SGL_CUDA(cudaFuncSetAttribute(nnls_masked_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                attr_done = true;
+            }
+            nnls_masked_big_kernel<<<(unsigned)n_parts, 32, smem, h->stream>>>(h->bparts.p, splits, F_out, h->gram_f_nojit.p, F_in,
+                                                                              X->colptr, mask->mptr, mask->mrec, X->ncol, k, KPV,
+                                                                              (float)L1, (float)L2, h->part.p);
+        }
+        LAUNCH_CHECK(h);
+    }
+    SGL_TRY(reduce_partials(h, h->part.p, n_parts, KPV, rowsum));
+    return SGL_OK;
+}
+
+static int dev_finish_d(sgl_handle* h, int k, double* d) {
+    finish_d_kernel<<<1, 128, 0, h->stream>>>(d, k, kp_of(k));
+    LAUNCH_CHECK(h);
+    return SGL_OK;
+}
+static int dev_scale(sgl_handle* h, float* F, int k, int64_t cols, const double* d) {
+    const int KPV = kp_of(k);
+    const int64_t n = cols * KPV;
+    if (n == 0) return SGL_OK;
+    scale_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(F, n, KPV, d);
+    LAUNCH_CHECK(h);
+    return SGL_OK;
+}
+static int dev_cor_sums(sgl_handle* h, const float* X, const float* Y, int k, int64_t cols, double* sums) {
+    const int KPV = kp_of(k);
+    const int64_t n = cols * KPV;
+    int64_t grid = (n + 256 * 8 - 1) / (256 * 8);
+    if (grid > 2 * h->sm_count) grid = 2 * h->sm_count;
+    if (grid < 1) grid = 1;
+    SGL_TRY(h->part.ensure((size_t)grid * 5));
+    cor_partial_kernel<<<(unsigned)grid, 256, 0, h->stream>>>(X, Y, n, h->part.p);
+    LAUNCH_CHECK(h);
+    return reduce_partials(h, h->part.p, grid, 5, sums);
+}
+
+static int scan_counts(sgl_handle* h, const int64_t* counts, int64_t n, int64_t* out) {
+    exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(counts, n, out);
+    LAUNCH_CHECK(h);
+    return SGL_OK;
+}
+
+static int mask_build(sgl_handle* h, const sgl_matrix* X, uint64_t seed, uint64_t inv_density, int mask_t,
+                      int64_t col_offset, int64_t row_offset, sgl_mask** out) {
+    if (inv_density == 0) return fail(SGL_EINVAL, "inv_density must be >= 1");
+    SGL_TRY(set_device(h));
+    sgl_mask* m = new sgl_mask();
+    m->X = X;
+    m->seed = seed;
+    m->inv_density = inv_density;
+    m->mask_t = mask_t;
+    m->col_offset = col_offset;
+    m->row_offset = row_offset;
+    MaskGen gen;
+    gen.seed = seed;
+    gen.mod = make_modp(inv_density);
+    gen.mask_t = mask_t;
+    gen.col_offset = col_offset;
+    gen.row_offset = row_offset;
+    int rc = SGL_OK;
+    unsigned long long* d_held = nullptr;
+    do {
+        if ((rc = h->counts.ensure((size_t)X->ncol + 2)) != SGL_OK) break;
+        if (cudaMalloc(&m->mptr, sizeof(int64_t) * (size_t)(X->ncol + 1)) != cudaSuccess ||
+            cudaMalloc(&m->rec_train, sizeof(uint2) * (size_t)(X->nnz > 0 ? X->nnz : 1)) != cudaSuccess ||
+            cudaMalloc(&d_held, sizeof(unsigned long long)) != cudaSuccess) {
+            rc = fail(SGL_ENOMEM, "mask build: cudaMalloc failed");
+            break;
+        }
+        cudaMemsetAsync(d_held, 0, sizeof(unsigned long long), h->stream);
+        const unsigned grid = blocks_for(X->ncol, 8);
+        if (X->ncol > 0) {
+            mask_lists_kernel<0><<<grid, 256, 0, h->stream>>>(gen, X->ncol, X->nrow, X->colptr, X->rec, h->counts.p, nullptr, nullptr);
+            ++h->launches;
+        }
+        exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->counts.p, X->ncol, m->mptr);
+        ++h->launches;
+        int64_t total = 0;
+        cudaMemcpyAsync(&total, m->mptr + X->ncol, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
+            rc = fail(SGL_ECUDA, "mask build: count pass failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        m->n_masked = total;
+        if (cudaMalloc(&m->mrec, sizeof(uint2) * (size_t)(total > 0 ? total : 1)) != cudaSuccess) {
+            rc = fail(SGL_ENOMEM, "mask build: cudaMalloc(%lld records) failed", (long long)total);
+            break;
+        }
+        if (X->ncol > 0) {
+            mask_lists_kernel<1><<<grid, 256, 0, h->stream>>>(gen, X->ncol, X->nrow, X->colptr, X->rec, nullptr, m->mptr, m->mrec);
+            ++h->launches;
+            mask_records_kernel<<<grid, 256, 0, h->stream>>>(gen, X->ncol, X->colptr, X->rec, m->rec_train, d_held);
+            ++h->launches;
+        }
+        unsigned long long held = 0;
+        cudaMemcpyAsync(&held, d_held, sizeof(held), cudaMemcpyDeviceToHost, h->stream);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
+            rc = fail(SGL_ECUDA, "mask build: fill pass failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        m->n_masked_nz = (int64_t)held;
+    } while (0);
+    if (d_held) cudaFree(d_held);
+    if (rc != SGL_OK) {
+        mask_release(m);
+        return rc;
+    }
+    *out = m;
+    return SGL_OK;
+}
+
+// sum of per-column losses -> loss_sum[0]
+static int dev_mse(sgl_handle* h, const sgl_matrix* A, const sgl_mask* mask, const float* W, const double* d, const float* H,
+                   int k, int which, double* loss_sum) {
+    const int KPV = kp_of(k);
+    if (which == 0 && !mask) return fail(SGL_EINVAL, "test MSE needs a mask");
+    if (mask && mask->mask_t != 0) return fail(SGL_EINVAL, "MSE needs the cell-column mask (mask_t = 0)");
+    if (A->ncol == 0) {
+        SGL_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), h->stream));
+        return SGL_OK;
+    }
+    SGL_TRY(h->losses.ensure((size_t)A->ncol));
+    SGL_TRY(h->gram_w.ensure((size_t)KPV * KPV));
+    if (which == 1) SGL_TRY(dev_gram(h, W, k, A->nrow, h->gram_w.p, false));
+    const unsigned grid = blocks_for(A->ncol, 4);
+    DISPATCH_KP(KPV, (mse_kernel<KP><<<grid, 128, 0, h->stream>>>(A->colptr, A->rec, mask ? mask->mptr : nullptr,
+                                                                  mask ? mask->mrec : nullptr, W, d, H, h->gram_w.p, A->nrow,
+                                                                  A->ncol, k, which, h->losses.p)));
+    LAUNCH_CHECK(h);
+    return reduce_partials(h, h->losses.p, A->ncol, 1, loss_sum);
+}
+
+static int factor_upload(sgl_handle* h, const double* host, int k, int64_t cols, float* dev) {
+    const int KPV = kp_of(k);
+    const size_t n = (size_t)k * (size_t)cols;
+    if (n == 0) return SGL_OK;
+    double* tmp = nullptr;
+    SGL_CUDA(cudaMalloc(&tmp, sizeof(double) * n));
+    cudaMemcpyAsync(tmp, host, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream);
+    factor_to_dev_kernel<<<blocks_for(cols * KPV, 256), 256, 0, h->stream>>>(tmp, k, KPV, cols, dev);
+    ++h->launches;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(SGL_ECUDA, "factor upload: %s", cudaGetErrorString(e));
+    return SGL_OK;
+}
+static int factor_download(sgl_handle* h, const float* dev, int k, int64_t cols, double* host) {
+    const int KPV = kp_of(k);
+    const size_t n = (size_t)k * (size_t)cols;
+    if (n == 0) return SGL_OK;
+    double* tmp = nullptr;
+    SGL_CUDA(cudaMalloc(&tmp, sizeof(double) * n));
+    factor_to_host_kernel<<<blocks_for((int64_t)n, 256), 256, 0, h->stream>>>(dev, k, KPV, cols, tmp);
+    ++h->launches;
+    cudaMemcpyAsync(host, tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(SGL_ECUDA, "factor download: %s", cudaGetErrorString(e));
+    return SGL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-facing drivers
+// ---------------------------------------------------------------------------------------------
+static int cached_upload(sgl_handle* h, const sgl_csc* chunks, int n, sgl_matrix** slot, sgl_mask** mask_slot,
+                         sgl_matrix** out) {
+    const uint64_t fp = fingerprint_chunks(chunks, n);
+    if (h->cache && *slot && (*slot)->fingerprint == fp) {
+        *out = *slot;
+        return SGL_OK;
+    }
+    if (*mask_slot) {
+        mask_release(*mask_slot);
+        *mask_slot = nullptr;
+    }
+    if (*slot) {
+        matrix_release(*slot);
+        *slot = nullptr;
+    }
+    sgl_matrix* m = nullptr;
+    SGL_TRY(matrix_upload(h, chunks, n, &m));
+    m->fingerprint = fp;
+    *slot = m;
+    *out = m;
+    return SGL_OK;
+}
+static int cached_mask(sgl_handle* h, const sgl_matrix* X, uint64_t seed, uint64_t inv, int mask_t, sgl_mask** slot,
+                       sgl_mask** out) {
+    if (*slot && (*slot)->X == X && (*slot)->seed == seed && (*slot)->inv_density == inv && (*slot)->mask_t == mask_t) {
+        *out = *slot;
+        return SGL_OK;
+    }
+    if (*slot) {
+        mask_release(*slot);
+        *slot = nullptr;
+    }
+    SGL_TRY(mask_build(h, X, seed, inv, mask_t, 0, 0, slot));
+    *out = *slot;
+    return SGL_OK;
+}
+
+struct FitBuffers {  // device state of one fit
+    float *W = nullptr, *H = nullptr, *Wprev = nullptr;
+    double *gram = nullptr, *dvec = nullptr, *sums = nullptr;
+    ~FitBuffers() {
+        if (W) cudaFree(W);
+        if (H) cudaFree(H);
+        if (Wprev) cudaFree(Wprev);
+        if (gram) cudaFree(gram);
+        if (dvec) cudaFree(dvec);
+        if (sums) cudaFree(sums);
+    }
+    int alloc(int KPV, int64_t m, int64_t n) {
+        if (cudaMalloc(&W, sizeof(float) * (size_t)m * KPV) != cudaSuccess || cudaMalloc(&H, sizeof(float) * (size_t)(n > 0 ? n : 1) * KPV) != cudaSuccess ||
+            cudaMalloc(&Wprev, sizeof(float) * (size_t)m * KPV) != cudaSuccess || cudaMalloc(&gram, sizeof(double) * KPV * KPV) != cudaSuccess ||
+            cudaMalloc(&dvec, sizeof(double) * KPV) != cudaSuccess || cudaMalloc(&sums, sizeof(double) * 8) != cudaSuccess)
+            return fail(SGL_ENOMEM, "fit: cudaMalloc of factor buffers failed (m=%lld n=%lld KP=%d)", (long long)m, (long long)n, KPV);
+        return SGL_OK;
+    }
+};
+
+static int check_shapes(const sgl_matrix* A, const sgl_matrix* At) {
+    if (A->nrow != At->ncol || A->ncol != At->nrow)
+        return fail(SGL_EINVAL, "At (%lld x %lld) is not the transpose shape of A (%lld x %lld)", (long long)At->nrow, (long long)At->ncol,
+                    (long long)A->nrow, (long long)A->ncol);
+    return SGL_OK;
+}
+
+// one ALS iteration: H update, scale, W update, scale, cor  (src/singlet.cpp:648-659 / 1108-1114)
+static int als_iteration(sgl_handle* h, FitBuffers& fb, sgl_matrix* A, sgl_matrix* At, const sgl_mask* mA, const sgl_mask* mAt, int k,
+                         double L1_w, double L1_h, double L2_w, double L2_h, const sgl_callbacks* cb, double* tol_out) {
+    const int KPV = kp_of(k);
+    const int64_t m = A->nrow, n = A->ncol;
+    SGL_CUDA(cudaMemcpyAsync(fb.Wprev, fb.W, sizeof(float) * (size_t)m * KPV, cudaMemcpyDeviceToDevice, h->stream));
+    SGL_TRY(dev_gram(h, fb.W, k, m, fb.gram, true));
+    SGL_TRY(dev_update(h, A, mA, fb.W, fb.H, k, fb.gram, L1_h, L2_h, fb.dvec));
+    SGL_TRY(dev_finish_d(h, k, fb.dvec));
+    SGL_TRY(dev_scale(h, fb.H, k, n, fb.dvec));
+    if (cb && cb->poll_interrupt && cb->poll_interrupt(cb->user)) return fail(SGL_EINTERRUPT, "interrupted");
+    SGL_TRY(dev_gram(h, fb.H, k, n, fb.gram, true));
+    SGL_TRY(dev_update(h, At, mAt, fb.H, fb.W, k, fb.gram, L1_w, L2_w, fb.dvec));
+    SGL_TRY(dev_finish_d(h, k, fb.dvec));
+    SGL_TRY(dev_scale(h, fb.W, k, m, fb.dvec));
+    SGL_TRY(dev_cor_sums(h, fb.W, fb.Wprev, k, m, fb.sums));
+    SGL_CUDA(cudaMemcpyAsync(h->pinned, fb.sums, sizeof(double) * 5, cudaMemcpyDeviceToHost, h->stream));
+    SGL_CUDA(cudaStreamSynchronize(h->stream));
+    *tol_out = sgl_cor_from_sums(h->pinned, (double)k * (double)m);
+    return SGL_OK;
+}
+
+static int fit_outputs(sgl_handle* h, FitBuffers& fb, int k, int64_t m, int64_t n, double* w, double* d, double* h_out) {
+    SGL_TRY(factor_download(h, fb.W, k, m, w));
+    SGL_TRY(factor_download(h, fb.H, k, n, h_out));
+    SGL_CUDA(cudaMemcpyAsync(h->pinned, fb.dvec, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
+    SGL_CUDA(cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < k; ++f) d[f] = h->pinned[f];
+    return SGL_OK;
+}
+
+static int fit_init(sgl_handle* h, FitBuffers& fb, int k, int64_t m, int64_t n, const double* w) {
+    const int KPV = kp_of(k);
+    SGL_TRY(fb.alloc(KPV, m, n));
+    SGL_TRY(factor_upload(h, w, k, m, fb.W));
+    SGL_CUDA(cudaMemsetAsync(fb.H, 0, sizeof(float) * (size_t)(n > 0 ? n : 1) * KPV, h->stream));  // h = 0 (:640)
+    std::vector<double> ones((size_t)KPV, 1.0);                                                   // d = 1 (:641)
+    SGL_CUDA(cudaMemcpyAsync(fb.dvec, ones.data(), sizeof(double) * KPV, cudaMemcpyHostToDevice, h->stream));
+    SGL_CUDA(cudaStreamSynchronize(h->stream));
+    return SGL_OK;
+}
+
+}  // namespace sgl
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+extern "C" {
+
+int sgl_version(void) { return 100; }
+const char* sgl_last_error(void) { return last_error().c_str(); }
+int sgl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int sgl_padded_rank(int k) { return (k >= 1 && k <= SGL_MAX_RANK) ? kp_of(k) : -1; }
+
+int sgl_create(int device, void* stream, sgl_handle** out) {
+    if (!out) return fail(SGL_EINVAL, "sgl_create: out is NULL");
+    int n = sgl_device_count();
+    if (n <= 0) return fail(SGL_ENODEVICE, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(SGL_EINVAL, "device %d out of range (found %d)", device, n);
+    cudaDeviceProp prop;
+    SGL_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(SGL_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    SGL_CUDA(cudaSetDevice(device));
+    sgl_handle* h = new sgl_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        h->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete h;
+            return fail(SGL_ECUDA, "cudaStreamCreate failed");
+        }
+        h->own_stream = true;
+    }
+    if (cudaMallocHost(&h->pinned, sizeof(double) * 256) != cudaSuccess) {
+        delete h;
+        return fail(SGL_ENOMEM, "cudaMallocHost failed");
+    }
+    *out = h;
+    return SGL_OK;
+}
+
+int sgl_destroy(sgl_handle* h) {
+    if (!h) return SGL_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    mask_release(h->cmA);
+    mask_release(h->cmAt);
+    matrix_release(h->cA);
+    matrix_release(h->cAt);
+    h->bparts.release(); h->gram_f.release(); h->gram_f_nojit.release(); h->inv_diag.release();
+    h->part.release(); h->scal.release(); h->losses.release(); h->gram_w.release(); h->counts.release();
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SGL_OK;
+}
+int sgl_set_cache(sgl_handle* h, int enabled) {
+    if (!h) return fail(SGL_EINVAL, "NULL handle");
+    h->cache = enabled != 0;
+    return SGL_OK;
+}
+int sgl_synchronize(sgl_handle* h) {
+    if (!h) return fail(SGL_EINVAL, "NULL handle");
+    SGL_CUDA(cudaStreamSynchronize(h->stream));
+    return SGL_OK;
+}
+int64_t sgl_launch_count(sgl_handle* h) { return h ? h->launches : 0; }
+
+// ---- c_nmf ---------------------------------------------------------------------------------
+int sgl_nmf(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, int nAt, double tol, uint16_t maxit, double L1_w,
+            double L1_h, double L2_w, double L2_h, int k, double* w, double* d, double* h_out, int32_t* iters_out,
+            double* tol_out, const sgl_callbacks* cb) {
+    if (!h || !w || !d || !h_out) return fail(SGL_EINVAL, "sgl_nmf: NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    sgl_matrix *A = nullptr, *At = nullptr;
+    SGL_TRY(cached_upload(h, A_, nA, &h->cA, &h->cmA, &A));
+    SGL_TRY(cached_upload(h, At_, nAt, &h->cAt, &h->cmAt, &At));
+    SGL_TRY(check_shapes(A, At));
+    FitBuffers fb;
+    SGL_TRY(fit_init(h, fb, k, A->nrow, A->ncol, w));
+    double tol_ = 1;
+    uint16_t iter_ = 0;
+    for (; iter_ < maxit && tol_ > tol; ++iter_) {  // src/singlet.cpp:647
+        SGL_TRY(als_iteration(h, fb, A, At, nullptr, nullptr, k, L1_w, L1_h, L2_w, L2_h, cb, &tol_));
+        if (cb && cb->on_iter) cb->on_iter(cb->user, iter_ + 1, tol_, NAN);
+        if (cb && cb->poll_interrupt && cb->poll_interrupt(cb->user)) return fail(SGL_EINTERRUPT, "interrupted");
+    }
+    if (iters_out) *iters_out = iter_;
+    if (tol_out) *tol_out = tol_;
+    return fit_outputs(h, fb, k, A->nrow, A->ncol, w, d, h_out);
+}
+
+// ---- c_ard_nmf -----------------------------------------------------------------------------
+int sgl_ard_nmf(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, int nAt, double tol, uint16_t maxit, double L1,
+                double L2, int k, double* w, double* d, double* h_out, uint64_t seed, uint64_t inv_density,
+                double overfit_threshold, uint16_t trace_test_mse, sgl_trace* tr, const sgl_callbacks* cb) {
+    if (!h || !w || !d || !h_out || !tr) return fail(SGL_EINVAL, "sgl_ard_nmf: NULL argument");
+    if (trace_test_mse == 0) return fail(SGL_EINVAL, "trace_test_mse must be >= 1 (the reference divides by it)");
+    if (inv_density == 0) return fail(SGL_EINVAL, "inv_density must be >= 1");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    sgl_matrix *A = nullptr, *At = nullptr;
+    SGL_TRY(cached_upload(h, A_, nA, &h->cA, &h->cmA, &A));
+    SGL_TRY(cached_upload(h, At_, nAt, &h->cAt, &h->cmAt, &At));
+    SGL_TRY(check_shapes(A, At));
+    sgl_mask *mA = nullptr, *mAt = nullptr;
+    SGL_TRY(cached_mask(h, A, seed, inv_density, 0, &h->cmA, &mA));
+    SGL_TRY(cached_mask(h, At, seed, inv_density, 1, &h->cmAt, &mAt));
+    FitBuffers fb;
+    SGL_TRY(fit_init(h, fb, k, A->nrow, A->ncol, w));
+    tr->length = 0;
+    auto push = [&](double mse, int it, double ft) {
+        if (tr->length >= tr->capacity) return;
+        const int q = tr->length;
+        tr->test_mse[q] = mse;
+        tr->iter[q] = it;
+        tr->tol[q] = ft;
+        double mn = tr->test_mse[0];
+        for (int t = 1; t <= q; ++t) mn = tr->test_mse[t] < mn ? tr->test_mse[t] : mn;
+        tr->score_overfit[q] = (mse - mn) / (mse + mn);
+        tr->length = q + 1;
+    };
+    auto test_mse = [&](double* out) -> int {
+        SGL_TRY(dev_mse(h, A, mA, fb.W, fb.dvec, fb.H, k, 0, fb.sums + 5));
+        SGL_CUDA(cudaMemcpyAsync(h->pinned + 8, fb.sums + 5, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        SGL_CUDA(cudaStreamSynchronize(h->stream));
+        *out = h->pinned[8] / (double)A->ncol;
+        return SGL_OK;
+    };
+    double tol_ = 1;
+    uint16_t iter_ = 0;
+    for (; iter_ < maxit && tol_ > tol; ++iter_) {  // src/singlet.cpp:1107
+        SGL_TRY(als_iteration(h, fb, A, At, mA, mAt, k, L1, L1, L2, L2, cb, &tol_));
+        double overfit = NAN;
+        bool stop = false;
+        if (iter_ % trace_test_mse == 0) {
+            double mse = 0;
+            SGL_TRY(test_mse(&mse));
+            push(mse, iter_, tol_);
+            overfit = tr->length ? tr->score_overfit[tr->length - 1] : NAN;
+            stop = overfit > overfit_threshold;
+        }
+        if (cb && cb->on_iter) cb->on_iter(cb->user, iter_ + 1, tol_, overfit);
+        if (stop) break;  // iter_ is not incremented on break (App. A-13)
+        if (cb && cb->poll_interrupt && cb->poll_interrupt(cb->user)) return fail(SGL_EINTERRUPT, "interrupted");
+    }
+    if (iter_ % trace_test_mse != 0) {
+        double mse = 0;
+        SGL_TRY(test_mse(&mse));
+        push(mse, iter_, tol_);
+    }
+    return fit_outputs(h, fb, k, A->nrow, A->ncol, w, d, h_out);
+}
+
+// ---- c_project_model / Rcpp_predict ----------------------------------------------------------
+static int project_common(sgl_handle* h, const sgl_csc* A_, int nA, const double* w, int64_t w_rows, int64_t w_cols, double L1,
+                          double L2, double* h_out, double* d_out, bool scaled) {
+    if (!h || !w || !h_out) return fail(SGL_EINVAL, "project: NULL argument");
+    SGL_TRY(set_device(h));
+    sgl_matrix* A = nullptr;
+    SGL_TRY(cached_upload(h, A_, nA, &h->cA, &h->cmA, &A));
+    const int64_t m = A->nrow;
+    // src/singlet.cpp:406 `if (w.rows() == A.rows()) w = w.transpose();`  (:351 for Rcpp_predict also
+    // requires w.cols() != A.rows())
+    const bool transpose = scaled ? (w_rows == m) : (w_rows == m && w_cols != m);
+    const int64_t k64 = transpose ? w_cols : w_rows;
+    const int64_t wm = transpose ? w_rows : w_cols;
+    if (wm != m) return fail(SGL_EINVAL, "'w' must share a common edge with the rows of 'A' (w is %lld x %lld, A has %lld rows)", (long long)w_rows, (long long)w_cols, (long long)m);
+    SGL_TRY(check_k((int)k64));
+    const int k = (int)k64;
+    std::vector<double> wk;
+    const double* wsrc = w;
+    if (transpose) {  // m x k column-major -> k x m column-major
+        wk.resize((size_t)k * (size_t)m);
+        for (int64_t g = 0; g < m; ++g)
+            for (int f = 0; f < k; ++f) wk[(size_t)g * k + f] = w[(size_t)f * m + g];
+        wsrc = wk.data();
+    }
+    FitBuffers fb;
+    SGL_TRY(fit_init(h, fb, k, m, A->ncol, wsrc));
+    if (scaled) {  // d = 1; scale(w, d)  (:407-408)
+        // row sums of the (host, FP64) w: k x m is small, the host already holds it
+        std::vector<double> wsum((size_t)k, 0.0);
+        for (int64_t g = 0; g < m; ++g)
+            for (int f = 0; f < k; ++f) wsum[(size_t)f] += wsrc[(size_t)g * k + f];
+        std::vector<double> dv((size_t)kp_of(k), 1.0);
+        for (int f = 0; f < k; ++f) dv[(size_t)f] = wsum[(size_t)f] + 1e-15;
+        SGL_CUDA(cudaMemcpyAsync(fb.dvec, dv.data(), sizeof(double) * dv.size(), cudaMemcpyHostToDevice, h->stream));
+        SGL_CUDA(cudaStreamSynchronize(h->stream));
+        SGL_TRY(dev_scale(h, fb.W, k, m, fb.dvec));
+    }
+    SGL_TRY(dev_gram(h, fb.W, k, m, fb.gram, true));
+    SGL_TRY(dev_update(h, A, nullptr, fb.W, fb.H, k, fb.gram, L1, L2, fb.dvec));
+    if (scaled) {
+        SGL_TRY(dev_finish_d(h, k, fb.dvec));
+        SGL_TRY(dev_scale(h, fb.H, k, A->ncol, fb.dvec));
+    }
+    SGL_TRY(factor_download(h, fb.H, k, A->ncol, h_out));
+    if (d_out) {
+        SGL_CUDA(cudaMemcpyAsync(h->pinned, fb.dvec, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
+        SGL_CUDA(cudaStreamSynchronize(h->stream));
+        for (int f = 0; f < k; ++f) d_out[f] = h->pinned[f];
+    }
+    return SGL_OK;
+}
+int sgl_project_model(sgl_handle* h, const sgl_csc* A, int nA, const double* w, int64_t w_rows, int64_t w_cols, double L1, double L2,
+                      double* h_out, double* d_out) {
+    return project_common(h, A, nA, w, w_rows, w_cols, L1, L2, h_out, d_out, true);
+}
+int sgl_predict(sgl_handle* h, const sgl_csc* A, int nA, const double* w, int64_t w_rows, int64_t w_cols, double L1, double L2,
+                double* h_out) {
+    return project_common(h, A, nA, w, w_rows, w_cols, L1, L2, h_out, nullptr, false);
+}
+
+// ---- rng test hooks --------------------------------------------------------------------------
+static int hash_hook(sgl_handle* h, uint64_t seed, uint64_t inv, const uint64_t* i, const uint64_t* j, int64_t n, uint64_t* out64,
+                     uint8_t* out8) {
+    if (!h || !i || !j || n < 0) return fail(SGL_EINVAL, "mask hook: bad argument");
+    if (n == 0) return SGL_OK;
+    SGL_TRY(set_device(h));
+    uint64_t *di = nullptr, *dj = nullptr, *dout = nullptr;
+    uint8_t* dout8 = nullptr;
+    int rc = SGL_OK;
+    if (cudaMalloc(&di, 8 * n) != cudaSuccess || cudaMalloc(&dj, 8 * n) != cudaSuccess || cudaMalloc(&dout, 8 * n) != cudaSuccess ||
+        cudaMalloc(&dout8, n) != cudaSuccess)
+        rc = fail(SGL_ENOMEM, "mask hook: cudaMalloc failed");
+    if (rc == SGL_OK) {
+        cudaMemcpyAsync(di, i, 8 * n, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(dj, j, 8 * n, cudaMemcpyHostToDevice, h->stream);
+        if (out64) {
+            hash_pairs_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(seed, di, dj, n, dout);
+            cudaMemcpyAsync(out64, dout, 8 * n, cudaMemcpyDeviceToHost, h->stream);
+        } else {
+            draw_pairs_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(seed, make_modp(inv), di, dj, n, dout8);
+            cudaMemcpyAsync(out8, dout8, n, cudaMemcpyDeviceToHost, h->stream);
+        }
+        ++h->launches;
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(SGL_ECUDA, "mask hook: %s", cudaGetErrorString(e));
+    }
+    if (di) cudaFree(di);
+    if (dj) cudaFree(dj);
+    if (dout) cudaFree(dout);
+    if (dout8) cudaFree(dout8);
+    return rc;
+}
+int sgl_mask_rand(sgl_handle* h, uint64_t seed, const uint64_t* i, const uint64_t* j, int64_t n, uint64_t* out) {
+    if (!out) return fail(SGL_EINVAL, "NULL out");
+    return hash_hook(h, seed, 1, i, j, n, out, nullptr);
+}
+int sgl_mask_draw(sgl_handle* h, uint64_t seed, uint64_t inv_density, const uint64_t* i, const uint64_t* j, int64_t n, uint8_t* out) {
+    if (!out) return fail(SGL_EINVAL, "NULL out");
+    if (inv_density == 0) return fail(SGL_EINVAL, "inv_density must be >= 1");
+    return hash_hook(h, seed, inv_density, i, j, n, nullptr, out);
+}
+
+// ---- device-level API ------------------------------------------------------------------------
+int sgl_matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl_matrix** out) {
+    if (!h || !out) return fail(SGL_EINVAL, "NULL argument");
+    return matrix_upload(h, chunks, n_chunks, out);
+}
+
+int sgl_matrix_synth(sgl_handle* h, int64_t m_genes, int64_t n_cells, double density, uint64_t data_seed, int orientation,
+                     int64_t col0, int64_t ncol, const float* values_table, sgl_matrix** out) {
+    if (!h || !out || !values_table) return fail(SGL_EINVAL, "NULL argument");
+    if (m_genes < 1 || m_genes > 0x7fffffffLL || n_cells < 1 || n_cells > 0xffffffffLL || density <= 0 || density > 0.5)
+        return fail(SGL_EINVAL, "synth: bad shape or density");
+    const int64_t total_cols = orientation == 0 ? n_cells : m_genes;
+    if (col0 < 0 || ncol < 0 || col0 + ncol > total_cols) return fail(SGL_EINVAL, "synth: column range out of bounds");
+    SGL_TRY(set_device(h));
+    SynthSpec sp;
+    sp.m = m_genes;
+    sp.n = n_cells;
+    sp.seed = data_seed;
+    int64_t S = (int64_t)std::floor(0.5 / density + 0.5);
+    if (S < 1) S = 1;
+    if (S > 65535) S = 65535;
+    sp.S = (uint32_t)S;
+    double q = density * (double)S * 4294967296.0;
+    if (q > 4294967295.0) q = 4294967295.0;
+    sp.q32 = (uint32_t)std::floor(q + 0.5);
+    for (int t = 0; t < 8; ++t) sp.table[t] = values_table[t];
+    sgl_matrix* m = new sgl_matrix();
+    m->nrow = orientation == 0 ? m_genes : n_cells;
+    m->ncol = ncol;
+    int rc = SGL_OK;
+    do {
+        if ((rc = h->counts.ensure((size_t)ncol + 2)) != SGL_OK) break;
+        if (cudaMalloc(&m->colptr, sizeof(int64_t) * (size_t)(ncol + 1)) != cudaSuccess) {
+            rc = fail(SGL_ENOMEM, "synth: cudaMalloc failed");
+            break;
+        }
+        const unsigned grid = blocks_for(ncol, 8);
+        if (ncol > 0) {
+            synth_kernel<0><<<grid, 256, 0, h->stream>>>(sp, orientation, col0, ncol, h->counts.p, nullptr, nullptr);
+            ++h->launches;
+        }
+        exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->counts.p, ncol, m->colptr);
+        ++h->launches;
+        int64_t total = 0;
+        cudaMemcpyAsync(&total, m->colptr + ncol, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) {
+            rc = fail(SGL_ECUDA, "synth: count pass failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        m->nnz = total;
+        if (cudaMalloc(&m->rec, sizeof(uint2) * (size_t)(total > 0 ? total : 1)) != cudaSuccess) {
+            rc = fail(SGL_ENOMEM, "synth: cudaMalloc(%lld records) failed", (long long)total);
+            break;
+        }
+        if (ncol > 0) {
+            synth_kernel<1><<<grid, 256, 0, h->stream>>>(sp, orientation, col0, ncol, nullptr, m->colptr, m->rec);
+            ++h->launches;
+        }
+        e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(SGL_ECUDA, "synth: fill pass failed: %s", cudaGetErrorString(e));
+    } while (0);
+    if (rc != SGL_OK) {
+        matrix_release(m);
+        return rc;
+    }
+    *out = m;
+    return SGL_OK;
+}
+
+int sgl_matrix_free(sgl_handle* h, sgl_matrix* m) {
+    if (h) cudaSetDevice(h->device);
+    matrix_release(m);
+    return SGL_OK;
+}
+int sgl_matrix_info(const sgl_matrix* m, int64_t* nrow, int64_t* ncol, int64_t* nnz) {
+    if (!m) return fail(SGL_EINVAL, "NULL matrix");
+    if (nrow) *nrow = m->nrow;
+    if (ncol) *ncol = m->ncol;
+    if (nnz) *nnz = m->nnz;
+    return SGL_OK;
+}
+int sgl_matrix_download(sgl_handle* h, const sgl_matrix* m, int32_t* p, int32_t* i, double* x) {
+    if (!h || !m || !p) return fail(SGL_EINVAL, "NULL argument");
+    if (m->nnz > 0x7fffffffLL) return fail(SGL_EINVAL, "matrix has %lld non-zeros: does not fit int32 pointers", (long long)m->nnz);
+    SGL_TRY(set_device(h));
+    std::vector<int64_t> cp((size_t)m->ncol + 1);
+    SGL_CUDA(cudaMemcpyAsync(cp.data(), m->colptr, sizeof(int64_t) * cp.size(), cudaMemcpyDeviceToHost, h->stream));
+    SGL_CUDA(cudaStreamSynchronize(h->stream));
+    for (size_t t = 0; t < cp.size(); ++t) p[t] = (int32_t)cp[t];
+    if (m->nnz > 0 && i && x) {
+        const int64_t PIECE = 32ll << 20;
+        const int64_t piece = m->nnz < PIECE ? m->nnz : PIECE;
+        int32_t* di = nullptr;
+        double* dx = nullptr;
+        if (cudaMalloc(&di, sizeof(int32_t) * piece) != cudaSuccess || cudaMalloc(&dx, sizeof(double) * piece) != cudaSuccess) {
+            if (di) cudaFree(di);
+            return fail(SGL_ENOMEM, "matrix download: cudaMalloc failed");
+        }
+        for (int64_t o = 0; o < m->nnz; o += piece) {
+            const int64_t len = (m->nnz - o) < piece ? (m->nnz - o) : piece;
+            unpack_records_kernel<<<blocks_for(len, 256), 256, 0, h->stream>>>(m->rec + o, len, di, dx);
+            ++h->launches;
+            cudaMemcpyAsync(i + o, di, sizeof(int32_t) * (size_t)len, cudaMemcpyDeviceToHost, h->stream);
+            cudaMemcpyAsync(x + o, dx, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, h->stream);
+            cudaStreamSynchronize(h->stream);
+        }
+        cudaFree(di);
+        cudaFree(dx);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(SGL_ECUDA, "matrix download: %s", cudaGetErrorString(e));
+    }
+    return SGL_OK;
+}
+
+int sgl_factor_upload(sgl_handle* h, const double* host, int k, int64_t cols, float* dev) {
+    if (!h || !host || !dev) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    return factor_upload(h, host, k, cols, dev);
+}
+int sgl_factor_download(sgl_handle* h, const float* dev, int k, int64_t cols, double* host) {
+    if (!h || !host || !dev) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    return factor_download(h, dev, k, cols, host);
+}
+
+int sgl_dev_gram(sgl_handle* h, const float* F, int k, int64_t cols, double* gram, int add_jitter) {
+    if (!h || !F || !gram) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    return dev_gram(h, F, k, cols, gram, add_jitter != 0);
+}
+int sgl_dev_gram_jitter(sgl_handle* h, int k, double* gram) {
+    if (!h || !gram) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    add_jitter_kernel<<<1, 128, 0, h->stream>>>(gram, k, kp_of(k));
+    LAUNCH_CHECK(h);
+    return SGL_OK;
+}
+int sgl_dev_update(sgl_handle* h, const sgl_matrix* X, const float* F_in, float* F_out, int k, const double* gram, double L1,
+                   double L2, double* rowsum) {
+    if (!h || !X || !F_in || !F_out || !gram || !rowsum) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    return dev_update(h, X, nullptr, F_in, F_out, k, gram, L1, L2, rowsum);
+}
+int sgl_dev_finish_d(sgl_handle* h, int k, double* d) {
+    if (!h || !d) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    return dev_finish_d(h, k, d);
+}
+int sgl_dev_scale(sgl_handle* h, float* F, int k, int64_t cols, const double* d) {
+    if (!h || !F || !d) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    return dev_scale(h, F, k, cols, d);
+}
+int sgl_dev_cor_sums(sgl_handle* h, const float* X, const float* Y, int k, int64_t cols, double* sums) {
+    if (!h || !X || !Y || !sums) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    return dev_cor_sums(h, X, Y, k, cols, sums);
+}
+double sgl_cor_from_sums(const double* s, double n) {
+    // 1 - (n sxy - sx sy) / sqrt((n sx2 - sx^2)(n sy2 - sy^2))   (src/singlet.cpp:196)
+    return 1 - (n * s[2] - s[0] * s[1]) / std::sqrt((n * s[3] - s[0] * s[0]) * (n * s[4] - s[1] * s[1]));
+}
+
+int sgl_mask_build(sgl_handle* h, const sgl_matrix* X, uint64_t seed, uint64_t inv_density, int mask_t, int64_t col_offset,
+                   int64_t row_offset, sgl_mask** out) {
+    if (!h || !X || !out) return fail(SGL_EINVAL, "NULL argument");
+    return mask_build(h, X, seed, inv_density, mask_t, col_offset, row_offset, out);
+}
+int sgl_mask_free(sgl_handle* h, sgl_mask* m) {
+    if (h) cudaSetDevice(h->device);
+    mask_release(m);
+    return SGL_OK;
+}
+int sgl_mask_info(const sgl_mask* m, int64_t* n_masked, int64_t* n_masked_nonzero) {
+    if (!m) return fail(SGL_EINVAL, "NULL mask");
+    if (n_masked) *n_masked = m->n_masked;
+    if (n_masked_nonzero) *n_masked_nonzero = m->n_masked_nz;
+    return SGL_OK;
+}
+int64_t sgl_mask_column(sgl_handle* h, const sgl_mask* m, int64_t col, int32_t* rows_out, int64_t capacity) {
+    if (!h || !m || col < 0 || col >= m->X->ncol) return fail(SGL_EINVAL, "mask column: bad argument");
+    if (set_device(h) != SGL_OK) return SGL_ECUDA;
+    int64_t be[2];
+    if (cudaMemcpyAsync(be, m->mptr + col, sizeof(be), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess)
+        return fail(SGL_ECUDA, "mask column: copy failed");
+    const int64_t cnt = be[1] - be[0];
+    if (rows_out && cnt > 0) {
+        const int64_t take = cnt < capacity ? cnt : capacity;
+        std::vector<uint2> tmp((size_t)take);
+        if (cudaMemcpyAsync(tmp.data(), m->mrec + be[0], sizeof(uint2) * (size_t)take, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess)
+            return fail(SGL_ECUDA, "mask column: copy failed");
+        for (int64_t t = 0; t < take; ++t) rows_out[t] = (int32_t)tmp[(size_t)t].x;
+    }
+    return cnt;
+}
+int sgl_dev_update_masked(sgl_handle* h, const sgl_matrix* X, const sgl_mask* mask, const float* F_in, float* F_out, int k,
+                          const double* gram, double L1, double L2, double* rowsum) {
+    if (!h || !X || !mask || !F_in || !F_out || !gram || !rowsum) return fail(SGL_EINVAL, "NULL argument");
+    if (mask->X != X) return fail(SGL_EINVAL, "mask was built for a different matrix");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    return dev_update(h, X, mask, F_in, F_out, k, gram, L1, L2, rowsum);
+}
+int sgl_dev_mse(sgl_handle* h, const sgl_matrix* A, const sgl_mask* mask, const float* W, const double* d, const float* H, int k,
+                int which, double* loss_sum) {
+    if (!h || !A || !W || !d || !H || !loss_sum) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    return dev_mse(h, A, mask, W, d, H, k, which, loss_sum);
+}
+
+}  // extern "C"

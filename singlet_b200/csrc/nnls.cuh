@@ -1,0 +1,397 @@
+// nnls.cuh -- sequential coordinate-descent NNLS with L1/L2 (reference src/singlet.cpp:229-250;
+// exact rules in SURVEY.md App. A-5), FP32 state.
+//
+// Two kernels:
+//  * nnls_cols_kernel<KP>: plain predict(). The Gram matrix is shared by every column, so ONE THREAD
+//    solves ONE COLUMN: b[KP] lives in registers (the coordinate loop is fully unrolled so all
+//    indices are static), x in a thread-private shared-memory column, and the Gram column a[:, i]
+//    is broadcast to the warp from shared memory (LDS.128, one wavefront per 4 values). This
+//    issues ~KP+20 instructions per coordinate step per 32 columns instead of ~10 per step per
+//    single column for a warp-per-column layout (an ~6x saving at KP = 32).
+//  * nnls_masked_kernel<KP>: predict_mask(). Every column has its own Gram a_i = a - W_M W_M^T
+//    (reference src/singlet.cpp:460-462), so ONE WARP solves ONE COLUMN: lane j holds rows
+//    j, j+32 of a_i in registers, builds the correction from the held-out rows, then runs the
+//    coordinate loop with shuffles.
+// Both write the row sums of the new solution (the local part of `scale`'s d, src/singlet.cpp:220)
+// as per-CTA double partials, reduced in a fixed order afterwards (deterministic).
+#pragma once
+#include "common.cuh"
+
+namespace sgl {
+
+constexpr int NNLS_MAX_SWEEPS = 100;  // uint8_t it < 100 (src/singlet.cpp:231)
+
+// one coordinate step on scalars; returns delta to apply as b -= a[:, i] * delta.
+// Mirrors App. A-5: diff = b_i / a_ii - L1 + L2 * x_i; clamp at zero; tol bookkeeping.
+__device__ __forceinline__ float cd_step(float bi, float inv_aii, float& xi, float L1, float L2, float& tol) {
+    float diff = bi * inv_aii;
+    diff -= L1;                 // L1 == 0 -> exact no-op
+    diff = fmaf(L2, xi, diff);  // L2 == 0 -> exact no-op
+    float delta;
+    if (-diff > xi) {
+        delta = -xi;  // x_i == 0 -> delta = -0: b unchanged, tol unchanged (matches `if (x != 0)`)
+        if (xi != 0.f) tol = 1.f;
+        xi = 0.f;
+    } else {
+        delta = diff;
+        if (diff != 0.f) {
+            xi += diff;
+            tol += fabsf(__fdividef(diff, xi + 1e-15f));
+        }
+    }
+    return delta;
+}
+
+// ----------------------------------------------------------------------------------------------
+// plain: thread per column
+// ----------------------------------------------------------------------------------------------
+template <int KP>
+struct NnlsCfg {
+    static constexpr int THREADS = (KP <= 32) ? 128 : 64;
+};
+
+template <int KP>
+__global__ void __launch_bounds__(NnlsCfg<KP>::THREADS)
+nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
+                 int splits, float* __restrict__ X,  // [ncol][KP] warm start in / solution out
+                 const float* __restrict__ gram_f,   // [KP][KP] float (symmetric)
+                 const float* __restrict__ inv_diag, // [KP]
+                 const int64_t* __restrict__ colptr, int64_t ncol, int k, float L1, float L2,
+                 double* __restrict__ rowsum_part)   // [gridDim.x][KP]
+{
+    constexpr int NT = NnlsCfg<KP>::THREADS;
+    __shared__ __align__(16) float sa[KP * KP];
+    __shared__ float sinv[KP];
+    __shared__ float sx[KP * NT];  // sx[i * NT + tid]
+    __shared__ double sred[NT / 32][KP];
+
+    for (int t = threadIdx.x; t < KP * KP; t += NT) sa[t] = gram_f[t];
+    for (int t = threadIdx.x; t < KP; t += NT) sinv[t] = inv_diag[t];
+    __syncthreads();
+
+    const int64_t col = (int64_t)blockIdx.x * NT + threadIdx.x;
+    const bool in_range = col < ncol;
+    const bool solve = in_range && (colptr[col] != colptr[col + 1]);  // empty columns are skipped (:340)
+
+    float b[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) b[j] = 0.f;
+    if (in_range) {
+        for (int s = 0; s < splits; ++s) {
+            const float4* src = reinterpret_cast<const float4*>(Bparts + ((int64_t)s * ncol + col) * KP);
+#pragma unroll
+            for (int j4 = 0; j4 < KP / 4; ++j4) {
+                const float4 v = src[j4];
+                b[4 * j4 + 0] += v.x; b[4 * j4 + 1] += v.y; b[4 * j4 + 2] += v.z; b[4 * j4 + 3] += v.w;
+            }
+        }
+        const float4* xs = reinterpret_cast<const float4*>(X + col * KP);
+#pragma unroll
+        for (int j4 = 0; j4 < KP / 4; ++j4) {
+            const float4 v = xs[j4];
+            sx[(4 * j4 + 0) * NT + threadIdx.x] = v.x; sx[(4 * j4 + 1) * NT + threadIdx.x] = v.y;
+            sx[(4 * j4 + 2) * NT + threadIdx.x] = v.z; sx[(4 * j4 + 3) * NT + threadIdx.x] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) sx[j * NT + threadIdx.x] = 0.f;
+    }
+
+    bool active = solve;
+    float tol = 1.f;
+    const float kf = (float)k;
+    for (int sweep = 0; sweep < NNLS_MAX_SWEEPS; ++sweep) {
+        active = active && (tol / kf > 1e-8f);
+        if (!__any_sync(0xffffffffu, active)) break;
+        tol = 0.f;
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+            if (i < k) {  // uniform
+                float xi = sx[i * NT + threadIdx.x];
+                float tl = tol;
+                float delta = cd_step(b[i], sinv[i], xi, L1, L2, tl);
+                if (active) {
+                    tol = tl;
+                    sx[i * NT + threadIdx.x] = xi;
+                } else {
+                    delta = 0.f;
+                }
+                const float4* ai = reinterpret_cast<const float4*>(sa + i * KP);
+#pragma unroll
+                for (int j4 = 0; j4 < KP / 4; ++j4) {
+                    const float4 a4 = ai[j4];
+                    b[4 * j4 + 0] = fmaf(-a4.x, delta, b[4 * j4 + 0]);
+                    b[4 * j4 + 1] = fmaf(-a4.y, delta, b[4 * j4 + 1]);
+                    b[4 * j4 + 2] = fmaf(-a4.z, delta, b[4 * j4 + 2]);
+                    b[4 * j4 + 3] = fmaf(-a4.w, delta, b[4 * j4 + 3]);
+                }
+            }
+        }
+    }
+
+    // write back + row sums of the solution (all columns of the block, skipped ones included:
+    // `scale` sums every column, src/singlet.cpp:220)
+    float xo[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) xo[j] = sx[j * NT + threadIdx.x];
+    if (solve) {
+        float4* xd = reinterpret_cast<float4*>(X + col * KP);
+#pragma unroll
+        for (int j4 = 0; j4 < KP / 4; ++j4) xd[j4] = make_float4(xo[4 * j4], xo[4 * j4 + 1], xo[4 * j4 + 2], xo[4 * j4 + 3]);
+    }
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+        const double s = warp_sum((double)xo[j]);
+        if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5][j] = s;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < KP; t += NT) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) s += sred[w][t];  // fixed order: deterministic
+        rowsum_part[(int64_t)blockIdx.x * KP + t] = s;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// generic fallback for KP = 128 (b and x both in thread-private shared memory; slow path for the
+// rare ranks above 64)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+nnls_cols_big_kernel(const float* __restrict__ Bparts, int splits, float* __restrict__ X,
+                     const float* __restrict__ gram_f, const float* __restrict__ inv_diag,
+                     const int64_t* __restrict__ colptr, int64_t ncol, int k, int KP, float L1, float L2,
+                     double* __restrict__ rowsum_part) {
+    extern __shared__ float sm[];
+    constexpr int NT = 32;
+    float* sb = sm;                  // [KP][NT]
+    float* sx = sm + (size_t)KP * NT;  // [KP][NT]
+    const int64_t col = (int64_t)blockIdx.x * NT + threadIdx.x;
+    const bool in_range = col < ncol;
+    const bool solve = in_range && (colptr[col] != colptr[col + 1]);
+    for (int j = 0; j < KP; ++j) {
+        float bj = 0.f, xj = 0.f;
+        if (in_range) {
+            for (int s = 0; s < splits; ++s) bj += Bparts[((int64_t)s * ncol + col) * KP + j];
+            xj = X[col * KP + j];
+        }
+        sb[j * NT + threadIdx.x] = bj;
+        sx[j * NT + threadIdx.x] = xj;
+    }
+    float tol = 1.f;
+    const float kf = (float)k;
+    if (solve) {
+        for (int sweep = 0; sweep < NNLS_MAX_SWEEPS && (tol / kf > 1e-8f); ++sweep) {
+            tol = 0.f;
+            for (int i = 0; i < k; ++i) {
+                float xi = sx[i * NT + threadIdx.x];
+                const float delta = cd_step(sb[i * NT + threadIdx.x], inv_diag[i], xi, L1, L2, tol);
+                sx[i * NT + threadIdx.x] = xi;
+                if (delta != 0.f)
+                    for (int j = 0; j < k; ++j) sb[j * NT + threadIdx.x] = fmaf(-gram_f[i * KP + j], delta, sb[j * NT + threadIdx.x]);
+            }
+        }
+    }
+    for (int j = 0; j < KP; ++j) {
+        const float xj = sx[j * NT + threadIdx.x];
+        if (solve) X[col * KP + j] = xj;
+        const double s = warp_sum((double)xj);
+        if (threadIdx.x == 0) rowsum_part[(int64_t)blockIdx.x * KP + j] = s;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// masked: warp per column, per-column Gram correction
+// ----------------------------------------------------------------------------------------------
+template <int KP>
+struct MaskedCfg {
+    static constexpr int RPL = (KP + 31) / 32;  // Gram rows per lane
+    static constexpr int WARPS = 4;
+};
+
+template <int KP>
+__global__ void __launch_bounds__(MaskedCfg<KP>::WARPS * 32)
+nnls_masked_kernel(const float* __restrict__ Bparts, int splits, float* __restrict__ X,
+                   const float* __restrict__ gram_f,   // [KP][KP] float, jitter-free part is fine (see below)
+                   const float* __restrict__ F,        // gather factor [rows][KP]
+                   const int64_t* __restrict__ colptr, // X's column pointers (empty-column skip)
+                   const int64_t* __restrict__ mptr,   // [ncol + 1] held-out list pointers
+                   const uint2* __restrict__ mrec,     // held-out records {row, value bits}
+                   int64_t ncol, int k, float L1, float L2, double* __restrict__ rowsum_part)
+{
+    constexpr int RPL = MaskedCfg<KP>::RPL;
+    constexpr int WARPS = MaskedCfg<KP>::WARPS;
+    __shared__ double sred[WARPS][KP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t col = (int64_t)blockIdx.x * WARPS + warp;
+    const bool in_range = col < ncol;
+    const bool solve = in_range && (colptr[col] != colptr[col + 1]);
+
+    // lane holds rows r = lane + 32*c of a_i: a[c][i] = a_i[r][i]
+    float a[RPL][KP];
+    float b[RPL], x[RPL];
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) {
+        const int r = lane + 32 * c;
+        b[c] = 0.f;
+        x[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < KP; ++i) a[c][i] = 0.f;
+        if (in_range && r < KP) {
+            for (int s = 0; s < splits; ++s) b[c] += Bparts[((int64_t)s * ncol + col) * KP + r];
+            x[c] = X[col * KP + r];
+        }
+    }
+
+    if (solve) {
+        // correction G_M = sum over held-out rows of f f^T  (reference: AAt(submat(w, idx)), :460-461)
+        const int64_t mb = mptr[col], me = mptr[col + 1];
+        for (int64_t p = mb; p < me; ++p) {
+            const int64_t row = (int64_t)mrec[p].x;
+            const float* fr = F + row * KP;
+            float mine[RPL];
+#pragma unroll
+            for (int c = 0; c < RPL; ++c) mine[c] = (lane + 32 * c < KP) ? fr[lane + 32 * c] : 0.f;
+            const float4* fr4 = reinterpret_cast<const float4*>(fr);
+#pragma unroll
+            for (int i4 = 0; i4 < KP / 4; ++i4) {
+                const float4 f4 = fr4[i4];  // uniform address: broadcast
+#pragma unroll
+                for (int c = 0; c < RPL; ++c) {
+                    a[c][4 * i4 + 0] = fmaf(mine[c], f4.x, a[c][4 * i4 + 0]);
+                    a[c][4 * i4 + 1] = fmaf(mine[c], f4.y, a[c][4 * i4 + 1]);
+                    a[c][4 * i4 + 2] = fmaf(mine[c], f4.z, a[c][4 * i4 + 2]);
+                    a[c][4 * i4 + 3] = fmaf(mine[c], f4.w, a[c][4 * i4 + 3]);
+                }
+            }
+        }
+        // a_i = (G + eps I) - (G_M + eps I): the jitters cancel (App. A-11), so subtract from the
+        // jitter-free FP32 copy of G.
+        float inv[RPL];
+#pragma unroll
+        for (int c = 0; c < RPL; ++c) {
+            const int r = lane + 32 * c;
+            inv[c] = 0.f;
+            if (r < KP) {
+#pragma unroll
+                for (int i = 0; i < KP; ++i) a[c][i] = gram_f[r * KP + i] - a[c][i];
+            }
+        }
+        // diagonal reciprocals: a_i[r][r] is element a[c][r] of the lane owning row r
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+            const float dia = a[i / 32][i];  // valid on lane i % 32
+            if ((i & 31) == lane) inv[i / 32] = 1.0f / dia;
+        }
+
+        float tol = 1.f;
+        const float kf = (float)k;
+        for (int sweep = 0; sweep < NNLS_MAX_SWEEPS && (tol / kf > 1e-8f); ++sweep) {
+            tol = 0.f;
+#pragma unroll
+            for (int i = 0; i < KP; ++i) {
+                if (i < k) {  // uniform
+                    const int owner = i & 31, c_own = i >> 5;
+                    const float bi = __shfl_sync(0xffffffffu, b[c_own], owner);
+                    float xi = __shfl_sync(0xffffffffu, x[c_own], owner);
+                    const float iv = __shfl_sync(0xffffffffu, inv[c_own], owner);
+                    const float delta = cd_step(bi, iv, xi, L1, L2, tol);  // redundantly on all lanes
+                    if (lane == owner) x[c_own] = xi;
+#pragma unroll
+                    for (int c = 0; c < RPL; ++c) b[c] = fmaf(-a[c][i], delta, b[c]);
+                }
+            }
+        }
+    }
+
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) {
+        const int r = lane + 32 * c;
+        if (r < KP) {
+            if (solve) X[col * KP + r] = x[c];
+            sred[warp][r] = in_range ? (double)x[c] : 0.0;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < KP; t += WARPS * 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) s += sred[w][t];
+        rowsum_part[(int64_t)blockIdx.x * KP + t] = s;
+    }
+}
+
+// generic masked fallback for KP = 128: a_i, b, x in shared memory (one warp per CTA, padded rows)
+__global__ void __launch_bounds__(32)
+nnls_masked_big_kernel(const float* __restrict__ Bparts, int splits, float* __restrict__ X,
+                       const float* __restrict__ gram_f, const float* __restrict__ F,
+                       const int64_t* __restrict__ colptr, const int64_t* __restrict__ mptr,
+                       const uint2* __restrict__ mrec, int64_t ncol, int k, int KP, float L1, float L2,
+                       double* __restrict__ rowsum_part) {
+    extern __shared__ float sm[];
+    const int LD = KP + 1;
+    float* sa = sm;                      // [KP][LD]
+    float* sb = sm + (size_t)KP * LD;    // [KP]
+    float* sx = sb + KP;                 // [KP]
+    float* sinv = sx + KP;               // [KP]
+    const int lane = threadIdx.x;
+    const int64_t col = blockIdx.x;
+    const bool solve = colptr[col] != colptr[col + 1];
+    for (int r = lane; r < KP; r += 32) {
+        float bj = 0.f;
+        for (int s = 0; s < splits; ++s) bj += Bparts[((int64_t)s * ncol + col) * KP + r];
+        sb[r] = bj;
+        sx[r] = X[col * KP + r];
+        for (int i = 0; i < KP; ++i) sa[r * LD + i] = 0.f;
+    }
+    __syncwarp();
+    if (solve) {
+        for (int64_t p = mptr[col]; p < mptr[col + 1]; ++p) {
+            const float* fr = F + (int64_t)mrec[p].x * KP;
+            for (int r = lane; r < k; r += 32) {
+                const float mine = fr[r];
+                for (int i = 0; i < k; ++i) sa[r * LD + i] = fmaf(mine, fr[i], sa[r * LD + i]);
+            }
+        }
+        for (int r = lane; r < KP; r += 32) {
+            for (int i = 0; i < KP; ++i) sa[r * LD + i] = gram_f[r * KP + i] - sa[r * LD + i];
+            sinv[r] = 1.0f / sa[r * LD + r];
+        }
+        __syncwarp();
+        float tol = 1.f;
+        const float kf = (float)k;
+        for (int sweep = 0; sweep < NNLS_MAX_SWEEPS && (tol / kf > 1e-8f); ++sweep) {
+            tol = 0.f;
+            for (int i = 0; i < k; ++i) {
+                float xi = sx[i];
+                const float delta = cd_step(sb[i], sinv[i], xi, L1, L2, tol);
+                __syncwarp();
+                if (lane == 0) sx[i] = xi;
+                for (int r = lane; r < k; r += 32) sb[r] = fmaf(-sa[r * LD + i], delta, sb[r]);
+                __syncwarp();
+            }
+        }
+    }
+    for (int r = lane; r < KP; r += 32) {
+        if (solve) X[col * KP + r] = sx[r];
+        rowsum_part[(int64_t)blockIdx.x * KP + r] = (double)sx[r];
+    }
+}
+
+// deterministic fixed-order reduction of per-CTA double partials: out[j] = sum_p part[p][j]
+__global__ void reduce_partials_kernel(const double* __restrict__ part, int64_t n_parts, int width,
+                                       double* __restrict__ out) {
+    __shared__ double sm[256];
+    const int j = blockIdx.x;  // one CTA per output element
+    double s = 0.0;
+    for (int64_t p = threadIdx.x; p < n_parts; p += blockDim.x) s += part[p * width + j];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[j] = sm[0];
+}
+
+}  // namespace sgl
