@@ -76,8 +76,16 @@ int sgl_destroy(sgl_handle* h);
  * passed again (a CV sweep makes dozens of calls on one matrix). Default on. */
 int sgl_set_cache(sgl_handle* h, int enabled);
 int sgl_synchronize(sgl_handle* h);
+/* the cudaStream_t all work of this handle is enqueued on */
+void* sgl_stream(sgl_handle* h);
 /* kernel launches issued through this handle so far (bench.py's gpu_launches) */
 int64_t sgl_launch_count(sgl_handle* h);
+
+/* Per-kernel-kind device timing with CUDA events on the handle's stream (kind 0 = SpMM, 1 = NNLS,
+ * 2 = Gram, 3 = other). sgl_profile_read synchronises, returns summed milliseconds, launch counts and
+ * algorithmic bytes per kind since the last read, and resets them. */
+int sgl_profile(sgl_handle* h, int enable);
+int sgl_profile_read(sgl_handle* h, double* ms4, int64_t* counts4, int64_t* bytes4);
 
 /* ---- host-facing entry points (one per reference routine) -------------------------------- */
 

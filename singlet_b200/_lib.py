@@ -53,7 +53,10 @@ SYMBOLS = [
     ("sgl_destroy", _i32, [_vp]),
     ("sgl_set_cache", _i32, [_vp, _i32]),
     ("sgl_synchronize", _i32, [_vp]),
+    ("sgl_stream", _vp, [_vp]),
     ("sgl_launch_count", _i64, [_vp]),
+    ("sgl_profile", _i32, [_vp, _i32]),
+    ("sgl_profile_read", _i32, [_vp, _vp, _vp, _vp]),
     ("sgl_nmf", _i32, [_vp, _vp, _i32, _vp, _i32, _dbl, _u16, _dbl, _dbl, _dbl, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("sgl_ard_nmf", _i32, [_vp, _vp, _i32, _vp, _i32, _dbl, _u16, _dbl, _dbl, _i32, _vp, _vp, _vp, _u64, _u64, _dbl, _u16,
                            _vp, _vp]),

@@ -164,6 +164,15 @@ __device__ __forceinline__ uint2 ldg_stream_u2(const uint2* p) {
     return r;
 }
 
+// ask L2 to fetch `count` 8-byte records starting at p (rounded out to 16-byte granules)
+__device__ __forceinline__ void l2_prefetch_records(const uint2* p, int32_t count) {
+    if (count <= 0) return;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uintptr_t a0 = a & ~(uintptr_t)15;
+    const uint32_t bytes = (uint32_t)(((a + (uintptr_t)count * 8 + 15) & ~(uintptr_t)15) - a0);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

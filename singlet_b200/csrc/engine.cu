@@ -94,6 +94,11 @@ struct sgl_handle {
     DevBuf<double> part, scal, losses, gram_w;
     DevBuf<int64_t> counts;
     double* pinned = nullptr;  // 64 doubles of pinned host scratch
+    // optional per-kernel-kind event timing (bench.py's roofline numbers are measured live with it)
+    bool profiling = false;
+    struct Span { int kind; cudaEvent_t a, b; int64_t bytes; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
     // upload cache (host-facing entry points)
     sgl_matrix* cA = nullptr;
     sgl_matrix* cAt = nullptr;
@@ -109,6 +114,33 @@ namespace sgl {
         cudaError_t _e = cudaGetLastError();                                                        \
         if (_e != cudaSuccess) return fail(SGL_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
+
+enum { PK_SPMM = 0, PK_NNLS = 1, PK_GRAM = 2, PK_OTHER = 3, PK_KINDS = 4 };
+static cudaEvent_t prof_event(sgl_handle* h) {
+    if (!h->event_pool.empty()) {
+        cudaEvent_t e = h->event_pool.back();
+        h->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {  // records an event pair around the launches issued in its lifetime
+    sgl_handle* h;
+    size_t idx = 0;
+    bool on;
+    ProfScope(sgl_handle* h_, int kind, int64_t bytes) : h(h_), on(h_->profiling) {
+        if (!on) return;
+        sgl_handle::Span sp{kind, prof_event(h), prof_event(h), bytes};
+        cudaEventRecord(sp.a, h->stream);
+        idx = h->spans.size();
+        h->spans.push_back(sp);
+    }
+    ~ProfScope() {
+        if (on) cudaEventRecord(h->spans[idx].b, h->stream);
+    }
+};
 
 static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
@@ -298,6 +330,7 @@ static int reduce_partials(sgl_handle* h, const double* part, int64_t n_parts, i
 
 static int dev_gram(sgl_handle* h, const float* F, int k, int64_t cols, double* gram, bool jitter) {
     const int KPV = kp_of(k);
+    ProfScope ps(h, PK_GRAM, 4ll * k * cols);
     int tile_cols = 128;
     DISPATCH_KP(KPV, tile_cols = GramCfg<KP>::TILE_COLS);
     int64_t grid = (cols + tile_cols - 1) / tile_cols;
@@ -363,7 +396,12 @@ static int dev_update(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask,
     splits = (ti->n_tiles + tiles_per_split - 1) / tiles_per_split;
     SGL_TRY(h->bparts.ensure((size_t)splits * (size_t)X->ncol * KPV));
     const uint2* rec = mask ? mask->rec_train : X->rec;
-    DISPATCH_KP(KPV, SGL_TRY(launch_spmm<KP>(h, X, rec, *ti, F_in, h->bparts.p, splits, tiles_per_split)));
+    {
+        // algorithmic bytes of this launch: 8*nnz + 4*(ncol+1) + 4*k*nrow + 4*k*ncol
+        ProfScope ps(h, PK_SPMM, 8 * X->nnz + 4 * (X->ncol + 1) + 4ll * k * X->nrow + 4ll * k * X->ncol);
+        DISPATCH_KP(KPV, SGL_TRY(launch_spmm<KP>(h, X, rec, *ti, F_in, h->bparts.p, splits, tiles_per_split)));
+    }
+    ProfScope ps_nnls(h, PK_NNLS, 0);
 
     int64_t n_parts = 0;
     if (!mask) {
@@ -742,6 +780,8 @@ int sgl_destroy(sgl_handle* h) {
     matrix_release(h->cAt);
     h->bparts.release(); h->gram_f.release(); h->gram_f_nojit.release(); h->inv_diag.release();
     h->part.release(); h->scal.release(); h->losses.release(); h->gram_w.release(); h->counts.release();
+    for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -758,6 +798,30 @@ int sgl_synchronize(sgl_handle* h) {
     return SGL_OK;
 }
 int64_t sgl_launch_count(sgl_handle* h) { return h ? h->launches : 0; }
+void* sgl_stream(sgl_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int sgl_profile(sgl_handle* h, int enable) {
+    if (!h) return fail(SGL_EINVAL, "NULL handle");
+    h->profiling = enable != 0;
+    return SGL_OK;
+}
+int sgl_profile_read(sgl_handle* h, double* ms, int64_t* counts, int64_t* bytes) {
+    if (!h || !ms || !counts || !bytes) return fail(SGL_EINVAL, "NULL argument");
+    SGL_CUDA(cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < PK_KINDS; ++q) { ms[q] = 0; counts[q] = 0; bytes[q] = 0; }
+    for (auto& sp : h->spans) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) {
+            ms[sp.kind] += t;
+            counts[sp.kind] += 1;
+            bytes[sp.kind] += sp.bytes;
+        }
+        h->event_pool.push_back(sp.a);
+        h->event_pool.push_back(sp.b);
+    }
+    h->spans.clear();
+    return SGL_OK;
+}
 
 // ---- c_nmf ---------------------------------------------------------------------------------
 int sgl_nmf(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, int nAt, double tol, uint16_t maxit, double L1_w,

@@ -48,10 +48,35 @@ __device__ __forceinline__ float cd_step(float bi, float inv_aii, float& xi, flo
 template <int KP>
 struct NnlsCfg {
     static constexpr int THREADS = (KP <= 32) ? 128 : 64;
+    static constexpr int MIN_CTAS = (KP <= 32) ? 4 : 3;  // register cap: 128 (KP<=32) / 170 (KP=64)
 };
 
+// branch-free coordinate step (same arithmetic as cd_step): returns MINUS the delta, i.e. the
+// multiplier m of  b += a[:, i] * m.
+__device__ __forceinline__ float cd_step_nb(float bi, float inv_aii, float& xi, float L1, float L2, float& tol) {
+    const float diff = fmaf(L2, xi, bi * inv_aii - L1);
+    const bool clamp = (-diff > xi);
+    const float xnew = clamp ? 0.f : xi + diff;
+    const float term = fabsf(__fdividef(diff, xnew + 1e-15f));  // diff == 0 -> 0
+    tol = clamp ? ((xi != 0.f) ? 1.f : tol) : tol + term;
+    const float m = clamp ? xi : -diff;
+    xi = xnew;
+    return m;
+}
+
+__device__ __forceinline__ void ffma2_bcast(unsigned long long& acc, unsigned long long w, float v) {
+    unsigned long long vv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(vv) : "f"(v));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(vv));
+}
+__device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((uint32_t)(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+
 template <int KP>
-__global__ void __launch_bounds__(NnlsCfg<KP>::THREADS)
+__global__ void __launch_bounds__(NnlsCfg<KP>::THREADS, NnlsCfg<KP>::MIN_CTAS)
 nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
                  int splits, float* __restrict__ X,  // [ncol][KP] warm start in / solution out
                  const float* __restrict__ gram_f,   // [KP][KP] float (symmetric)
@@ -60,6 +85,7 @@ nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
                  double* __restrict__ rowsum_part)   // [gridDim.x][KP]
 {
     constexpr int NT = NnlsCfg<KP>::THREADS;
+    constexpr int KP2 = (KP + 1) / 2 * 2;
     __shared__ __align__(16) float sa[KP * KP];
     __shared__ float sinv[KP];
     __shared__ float sx[KP * NT];  // sx[i * NT + tid]
@@ -73,33 +99,40 @@ nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
     const bool in_range = col < ncol;
     const bool solve = in_range && (colptr[col] != colptr[col + 1]);  // empty columns are skipped (:340)
 
-    float b[KP];
+    // b as packed FP32 pairs so that the rank-1 update runs on FFMA2
+    unsigned long long b2[KP2 / 2];
+    {
+        float b[KP];
 #pragma unroll
-    for (int j = 0; j < KP; ++j) b[j] = 0.f;
-    if (in_range) {
-        for (int s = 0; s < splits; ++s) {
-            const float4* src = reinterpret_cast<const float4*>(Bparts + ((int64_t)s * ncol + col) * KP);
+        for (int j = 0; j < KP; ++j) b[j] = 0.f;
+        if (in_range) {
+            for (int s = 0; s < splits; ++s) {
+                const float4* src = reinterpret_cast<const float4*>(Bparts + ((int64_t)s * ncol + col) * KP);
+#pragma unroll
+                for (int j4 = 0; j4 < KP / 4; ++j4) {
+                    const float4 v = src[j4];
+                    b[4 * j4 + 0] += v.x; b[4 * j4 + 1] += v.y; b[4 * j4 + 2] += v.z; b[4 * j4 + 3] += v.w;
+                }
+            }
+            const float4* xs = reinterpret_cast<const float4*>(X + col * KP);
 #pragma unroll
             for (int j4 = 0; j4 < KP / 4; ++j4) {
-                const float4 v = src[j4];
-                b[4 * j4 + 0] += v.x; b[4 * j4 + 1] += v.y; b[4 * j4 + 2] += v.z; b[4 * j4 + 3] += v.w;
+                const float4 v = xs[j4];
+                sx[(4 * j4 + 0) * NT + threadIdx.x] = v.x; sx[(4 * j4 + 1) * NT + threadIdx.x] = v.y;
+                sx[(4 * j4 + 2) * NT + threadIdx.x] = v.z; sx[(4 * j4 + 3) * NT + threadIdx.x] = v.w;
             }
-        }
-        const float4* xs = reinterpret_cast<const float4*>(X + col * KP);
+        } else {
 #pragma unroll
-        for (int j4 = 0; j4 < KP / 4; ++j4) {
-            const float4 v = xs[j4];
-            sx[(4 * j4 + 0) * NT + threadIdx.x] = v.x; sx[(4 * j4 + 1) * NT + threadIdx.x] = v.y;
-            sx[(4 * j4 + 2) * NT + threadIdx.x] = v.z; sx[(4 * j4 + 3) * NT + threadIdx.x] = v.w;
+            for (int j = 0; j < KP; ++j) sx[j * NT + threadIdx.x] = 0.f;
         }
-    } else {
 #pragma unroll
-        for (int j = 0; j < KP; ++j) sx[j * NT + threadIdx.x] = 0.f;
+        for (int j2 = 0; j2 < KP / 2; ++j2) b2[j2] = pack2(b[2 * j2], b[2 * j2 + 1]);
     }
 
     bool active = solve;
     float tol = 1.f;
     const float kf = (float)k;
+    const uint32_t sa_addr = smem_u32(sa);
     for (int sweep = 0; sweep < NNLS_MAX_SWEEPS; ++sweep) {
         active = active && (tol / kf > 1e-8f);
         if (!__any_sync(0xffffffffu, active)) break;
@@ -107,23 +140,19 @@ nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
 #pragma unroll
         for (int i = 0; i < KP; ++i) {
             if (i < k) {  // uniform
-                float xi = sx[i * NT + threadIdx.x];
-                float tl = tol;
-                float delta = cd_step(b[i], sinv[i], xi, L1, L2, tl);
-                if (active) {
-                    tol = tl;
-                    sx[i * NT + threadIdx.x] = xi;
-                } else {
-                    delta = 0.f;
-                }
-                const float4* ai = reinterpret_cast<const float4*>(sa + i * KP);
+                const float xi_old = sx[i * NT + threadIdx.x];
+                float xi = xi_old, tl = tol;
+                const float bi = (i & 1) ? hi32(b2[i >> 1]) : lo32(b2[i >> 1]);
+                float mult = cd_step_nb(bi, sinv[i], xi, L1, L2, tl);
+                mult = active ? mult : 0.f;
+                tol = active ? tl : tol;
+                if (active) sx[i * NT + threadIdx.x] = xi;
 #pragma unroll
                 for (int j4 = 0; j4 < KP / 4; ++j4) {
-                    const float4 a4 = ai[j4];
-                    b[4 * j4 + 0] = fmaf(-a4.x, delta, b[4 * j4 + 0]);
-                    b[4 * j4 + 1] = fmaf(-a4.y, delta, b[4 * j4 + 1]);
-                    b[4 * j4 + 2] = fmaf(-a4.z, delta, b[4 * j4 + 2]);
-                    b[4 * j4 + 3] = fmaf(-a4.w, delta, b[4 * j4 + 3]);
+                    unsigned long long a01, a23;
+                    asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a01), "=l"(a23) : "r"(sa_addr + (uint32_t)((i * KP + 4 * j4) * 4)));
+                    ffma2_bcast(b2[2 * j4 + 0], a01, mult);
+                    ffma2_bcast(b2[2 * j4 + 1], a23, mult);
                 }
             }
         }

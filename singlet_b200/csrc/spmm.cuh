@@ -27,12 +27,14 @@ template <int KP>
 struct SpmmCfg {
     static constexpr int LPN = (KP / 4 < 8) ? (KP / 4) : 8;  // lanes per non-zero
     static constexpr int FPL = KP / LPN;                     // factors per lane (4, 8 or 16)
-    static constexpr int NV = FPL / 4;                       // float4 per lane per non-zero
+    static constexpr int NV = FPL / 4;                       // 16-byte loads per lane per non-zero
     static constexpr int SLOTS = 32 / LPN;                   // non-zeros per warp step
     static constexpr int NC = (64 / FPL);                    // columns per warp (64 accumulator regs)
     static constexpr int WARPS = 16;
     static constexpr int COLS_PER_CTA = WARPS * NC;
-    static constexpr int UNR = 4;  // record loads in flight per lane
+    // record loads issued back to back before the first use: one group covers ~48 non-zeros, i.e. a
+    // typical (column, tile) sub-range, so each sub-range exposes one memory latency
+    static constexpr int UNR = (48 / SLOTS) < 2 ? 2 : (48 / SLOTS);
 };
 
 // rows per staged tile: two stages must fit in 227 KB of shared memory
@@ -41,6 +43,17 @@ static inline int spmm_tile_rows(int kp) {
     int rows = budget / (kp * 4);
     rows &= ~7;
     return rows;
+}
+
+// packed FP32 pair FMA (sm_100 FFMA2; SASS takes the scalar operand as a broadcast .F32):
+//   acc.{lo,hi} += w.{lo,hi} * v
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long w, float v) {
+    unsigned long long vv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(vv) : "f"(v));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(vv));
+}
+__device__ __forceinline__ void lds_2x64(uint32_t addr, unsigned long long& a, unsigned long long& b) {
+    asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
 
 template <int KP>
@@ -53,6 +66,7 @@ spmm_tiles_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ col
 {
     using C = SpmmCfg<KP>;
     constexpr int UNR = C::UNR;
+    constexpr int GROUP = UNR * C::SLOTS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage0 = reinterpret_cast<float*>(smem_raw);
     const size_t stage_floats = (size_t)rb_rows * KP;
@@ -86,68 +100,77 @@ spmm_tiles_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ col
         if (t_begin + 1 < t_end) issue(t_begin + 1);
     }
 
-    float acc[C::NC][C::FPL];
+    // accumulators: NC columns x FPL factors, as packed FP32 pairs
+    unsigned long long acc[C::NC][C::FPL / 2];
 #pragma unroll
     for (int j = 0; j < C::NC; ++j)
 #pragma unroll
-        for (int f = 0; f < C::FPL; ++f) acc[j][f] = 0.f;
+        for (int f = 0; f < C::FPL / 2; ++f) acc[j][f] = 0ull;
 
     // this lane's column (for the coalesced tile-pointer loads) and its record base
     const int64_t my_col = col0 + lane;
     const bool my_col_ok = (lane < C::NC) && (my_col < ncol);
     const int64_t my_base = my_col_ok ? colptr[my_col] : 0;
 
-    // tileptr[t][col] is both the end of tile t-1 and the start of tile t: keep one value per lane
-    // and fetch the next boundary one tile ahead of its use.
-    int32_t beg_l = 0, nxt_l = 0;
+    // tileptr[t][col] is both the end of tile t-1 and the start of tile t. Each lane (< NC) keeps the
+    // boundaries of its column three tiles deep so that, at the top of tile t, it can (a) fetch the
+    // boundary needed two tiles later and (b) ask L2 to prefetch the column's records of tile t+1
+    // with one bulk prefetch (the record loads of the next tile then hit L2 instead of HBM).
+    int32_t p0 = 0, p1 = 0, p2 = 0;  // tileptr[t], tileptr[t+1], tileptr[t+2]
     if (my_col_ok && t_begin < t_end) {
-        beg_l = tileptr[(int64_t)t_begin * ncol_pad + my_col];
-        nxt_l = tileptr[(int64_t)(t_begin + 1) * ncol_pad + my_col];
+        p0 = tileptr[(int64_t)t_begin * ncol_pad + my_col];
+        p1 = tileptr[(int64_t)(t_begin + 1) * ncol_pad + my_col];
+        p2 = (t_begin + 1 < t_end) ? tileptr[(int64_t)(t_begin + 2) * ncol_pad + my_col] : p1;
+        l2_prefetch_records(rec + my_base + p0, p1 - p0);
     }
 
     uint32_t phase0 = 0, phase1 = 0;
     for (int t = t_begin; t < t_end; ++t) {
         const int s = (t - t_begin) & 1;
-        const int32_t end_l = nxt_l;
-        if (my_col_ok && t + 1 < t_end) nxt_l = tileptr[(int64_t)(t + 2) * ncol_pad + my_col];
+        // per-lane (lanes < NC): first record of this column in tile t, and how many
+        const int64_t start_l = my_base + p0;
+        const int32_t cnt_l = p1 - p0;
+        int32_t p3 = p2;
+        if (my_col_ok) {
+            if (t + 2 < t_end) p3 = tileptr[(int64_t)(t + 3) * ncol_pad + my_col];
+            if (t + 1 < t_end) l2_prefetch_records(rec + my_base + p1, p2 - p1);
+        }
         mbar_wait(&bars[s], s ? phase1 : phase0);
         if (s) phase1 ^= 1u; else phase0 ^= 1u;
-        const float* tile = s ? stage1 : stage0;
-        const int32_t row_base = t * rb_rows;
+        // shared address of (row 0 of the matrix, chunk q) as seen through this tile: adding
+        // row * KP * 4 for any row of the tile lands inside the stage (32-bit wrap-around is fine)
+        const uint32_t tile_q = smem_u32(s ? stage1 : stage0) + (uint32_t)q * 16u - (uint32_t)(t * rb_rows) * (uint32_t)(KP * 4);
 
+        const uint32_t pad_row = (uint32_t)(t * rb_rows);  // a valid row of this tile
 #pragma unroll
         for (int j = 0; j < C::NC; ++j) {
-            const int64_t base = __shfl_sync(0xffffffffu, my_base, j);
-            const int32_t beg = __shfl_sync(0xffffffffu, beg_l, j);
-            const int32_t end = __shfl_sync(0xffffffffu, end_l, j);
-            const uint2* rp = rec + base;
-            // warp-uniform loop over groups of UNR warp steps; each step covers SLOTS records
-            for (int32_t s0 = beg; s0 < end; s0 += UNR * C::SLOTS) {
+            const int64_t start = __shfl_sync(0xffffffffu, start_l, j);
+            const int32_t n = __shfl_sync(0xffffffffu, cnt_l, j);
+            const uint2* lp = rec + start + g;  // this lane's first record
+            int32_t rem = n - g;                // records left for this lane's slot (may be <= 0)
+            for (int32_t done = 0; done < n; done += GROUP) {  // warp-uniform
+                // slots past the end of the sub-range gather a valid row with value 0 (adds +0)
                 uint2 r[UNR];
 #pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    const int32_t p = s0 + u * C::SLOTS + g;
-                    r[u] = (p < end) ? ldg_stream_u2(rp + p) : make_uint2((uint32_t)row_base, 0u);
-                }
+                for (int u = 0; u < UNR; ++u)
+                    r[u] = (rem > u * C::SLOTS) ? ldg_stream_u2(lp + u * C::SLOTS) : make_uint2(pad_row, 0u);
 #pragma unroll
                 for (int u = 0; u < UNR; ++u) {
-                    if (s0 + u * C::SLOTS < end) {  // uniform
-                        const float v = __uint_as_float(r[u].y);
-                        const float4* src =
-                            reinterpret_cast<const float4*>(tile + (size_t)((int32_t)r[u].x - row_base) * KP) + q;
+                    const float v = __uint_as_float(r[u].y);
+                    const uint32_t a = tile_q + r[u].x * (uint32_t)(KP * 4);
 #pragma unroll
-                        for (int c4 = 0; c4 < C::NV; ++c4) {
-                            const float4 w4 = src[c4 * C::LPN];
-                            acc[j][4 * c4 + 0] = fmaf(v, w4.x, acc[j][4 * c4 + 0]);
-                            acc[j][4 * c4 + 1] = fmaf(v, w4.y, acc[j][4 * c4 + 1]);
-                            acc[j][4 * c4 + 2] = fmaf(v, w4.z, acc[j][4 * c4 + 2]);
-                            acc[j][4 * c4 + 3] = fmaf(v, w4.w, acc[j][4 * c4 + 3]);
-                        }
+                    for (int c4 = 0; c4 < C::NV; ++c4) {
+                        unsigned long long w01, w23;
+                        lds_2x64(a + (uint32_t)(c4 * C::LPN * 16), w01, w23);
+                        ffma2(acc[j][2 * c4 + 0], w01, v);
+                        ffma2(acc[j][2 * c4 + 1], w23, v);
                     }
                 }
+                lp += GROUP;
+                rem -= GROUP;
             }
         }
-        beg_l = end_l;
+        p0 = p1; p1 = p2; p2 = p3;
         __syncthreads();  // every warp is done with stage s
         if (threadIdx.x == 0 && t + 2 < t_end) issue(t + 2);
     }
@@ -155,19 +178,25 @@ spmm_tiles_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ col
     // fold the SLOTS partial sums (lanes with equal q) and store
 #pragma unroll
     for (int j = 0; j < C::NC; ++j) {
+        float out[C::FPL];
 #pragma unroll
-        for (int f = 0; f < C::FPL; ++f) {
-            float v = acc[j][f];
+        for (int f = 0; f < C::FPL / 2; ++f) {
+            float lo = __uint_as_float((uint32_t)(acc[j][f] & 0xffffffffull));
+            float hi = __uint_as_float((uint32_t)(acc[j][f] >> 32));
 #pragma unroll
-            for (int o = C::LPN; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            acc[j][f] = v;
+            for (int o = C::LPN; o < 32; o <<= 1) {
+                lo += __shfl_xor_sync(0xffffffffu, lo, o);
+                hi += __shfl_xor_sync(0xffffffffu, hi, o);
+            }
+            out[2 * f] = lo;
+            out[2 * f + 1] = hi;
         }
         const int64_t col = col0 + j;
         if (g == 0 && col < ncol) {
             float4* dst = reinterpret_cast<float4*>(Bout + ((int64_t)blockIdx.y * ncol + col) * KP) + q;
 #pragma unroll
             for (int u = 0; u < C::NV; ++u)
-                dst[u * C::LPN] = make_float4(acc[j][4 * u + 0], acc[j][4 * u + 1], acc[j][4 * u + 2], acc[j][4 * u + 3]);
+                dst[u * C::LPN] = make_float4(out[4 * u + 0], out[4 * u + 1], out[4 * u + 2], out[4 * u + 3]);
         }
     }
 }

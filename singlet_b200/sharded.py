@@ -43,8 +43,11 @@ class CudaBackend:
         torch.cuda.set_device(device)
         self.device = torch.device("cuda", device)
         self._h = C.c_void_p()
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self.lib.sgl_create(device, C.c_void_p(stream), C.byref(self._h)))
+        # the library creates its stream; torch adopts it as the current stream so that tensor ops,
+        # NCCL collectives and CUDA events of this process are ordered with the library's kernels
+        _lib.check(self.lib.sgl_create(device, None, C.byref(self._h)))
+        self.stream = torch.cuda.ExternalStream(int(self.lib.sgl_stream(self._h)), device=self.device)
+        torch.cuda.set_stream(self.stream)
         self._mats, self._masks = [], []
 
     # -- memory -------------------------------------------------------------------------------
@@ -135,6 +138,15 @@ class CudaBackend:
 
     def launch_count(self):
         return int(self.lib.sgl_launch_count(self._h))
+
+    def profile(self, enable: bool):
+        _lib.check(self.lib.sgl_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """{kind: (ms, launches, algorithmic bytes)} since the last read (synchronises)."""
+        ms, cnt, byt = np.zeros(4), np.zeros(4, np.int64), np.zeros(4, np.int64)
+        _lib.check(self.lib.sgl_profile_read(self._h, ms.ctypes.data, cnt.ctypes.data, byt.ctypes.data))
+        return {name: (float(ms[q]), int(cnt[q]), int(byt[q])) for q, name in enumerate(("spmm", "nnls", "gram", "other"))}
 
     def synchronize(self):
         _lib.check(self.lib.sgl_synchronize(self._h))

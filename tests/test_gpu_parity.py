@@ -1,0 +1,261 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): mask / held-out index selection bit-exact; after matching
+factors by cosine, per-factor correlation >= 0.999; train/test MSE within 1e-4 relative.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import match_factors, min_factor_cor
+
+pytestmark = pytest.mark.gpu
+
+COR_MIN = 0.999
+MSE_RTOL = 1e-4
+
+
+def _mk(m, n, density, seed, empty_cols=()):
+    from singlet_b200 import synth
+
+    A = synth.synth_scipy(m, n, density, seed=seed).tolil()
+    for c in empty_cols:
+        A[:, c] = 0
+    A = A.tocsc()
+    A.eliminate_zeros()
+    A.sort_indices()
+    At = A.T.tocsc()
+    At.sort_indices()
+    return A, At
+
+
+def test_mask_hash_bit_exact(handle, oracle):
+    """rng::rand(i,j) and rng::draw on the device == reference hash (src/singlet.cpp:47-64, 91-95)."""
+    from singlet_b200 import _lib
+
+    rs = np.random.RandomState(0)
+    n = 200000
+    i = rs.randint(0, 2**40, size=n).astype(np.uint64)
+    j = rs.randint(0, 2**33, size=n).astype(np.uint64)
+    i[:6] = [0, 1, 7, 2699, 999999, 2**63 + 5]
+    j[:6] = [0, 0, 13, 13713, 29999, 2**62 + 1]
+    for seed in (0, 1, 123, 999, 2147483647, 1234567890123, 2**64 - 1):
+        out = np.zeros(n, np.uint64)
+        _lib.check(handle.lib.sgl_mask_rand(handle.ptr, seed, i.ctypes.data, j.ctypes.data, n, out.ctypes.data))
+        exp = np.array([oracle.rand2(seed, int(a), int(b)) for a, b in zip(i[:3000], j[:3000])], dtype=np.uint64)
+        assert np.array_equal(out[:3000], exp)
+        for inv in (1, 2, 20, 33, 65535, 65536, 10**9 + 7, 2**40 + 3):
+            d = np.zeros(n, np.uint8)
+            _lib.check(handle.lib.sgl_mask_draw(handle.ptr, seed, inv, i.ctypes.data, j.ctypes.data, n, d.ctypes.data))
+            assert np.array_equal(d.astype(bool), (out % np.uint64(inv)) == 0)
+
+
+def test_rng_known_answers_on_device(handle):
+    """SURVEY.md App. B.1 known-answer vectors (generated from the verbatim reference class)."""
+    from singlet_b200 import _lib
+
+    kat = {
+        (0, 0, 1): 2459528346506729745, (1, 1, 0): 6295464863713931364, (123, 7, 13): 9538636253944861798,
+        (999, 2699, 13713): 12937052898447939927, (2147483647, 999999, 29999): 7545449070027258386,
+        (1234567890123, 0, 0): 15671908682223407781,
+    }
+    for (seed, i, j), exp in kat.items():
+        ii, jj, out = np.array([i], np.uint64), np.array([j], np.uint64), np.zeros(1, np.uint64)
+        _lib.check(handle.lib.sgl_mask_rand(handle.ptr, seed, ii.ctypes.data, jj.ctypes.data, 1, out.ctypes.data))
+        assert int(out[0]) == exp
+
+
+def test_synth_device_matches_host():
+    """The device generator and the numpy restatement produce identical matrices (both orientations)."""
+    from singlet_b200 import synth
+    from singlet_b200.sharded import CudaBackend
+
+    be = CudaBackend(0)
+    try:
+        m, n, dens = 1234, 777, 0.05
+        A = synth.synth_scipy(m, n, dens)
+        tab = synth.values_table(m, dens)
+        h = be.synth(m, n, dens, synth.DATA_SEED, 0, 100, 500, tab)
+        p, i, x, nrow, ncol = be.matrix_to_host(h)
+        S = A[:, 100:600]
+        assert (nrow, ncol) == (m, 500)
+        assert np.array_equal(p, S.indptr) and np.array_equal(i, S.indices) and np.array_equal(x, S.data)
+        ht = be.synth(m, n, dens, synth.DATA_SEED, 1, 200, 900, tab)
+        p, i, x, nrow, ncol = be.matrix_to_host(ht)
+        T = A.T.tocsc()
+        T.sort_indices()
+        T = T[:, 200:1100]
+        assert (nrow, ncol) == (n, 900)
+        assert np.array_equal(p, T.indptr) and np.array_equal(i, T.indices) and np.array_equal(x, T.data)
+    finally:
+        be.close()
+
+
+@pytest.mark.parametrize("k", [1, 3, 8, 10, 20, 32, 40, 64, 100])
+def test_predict_matches_oracle(handle, oracle, k):
+    """One H update (Rcpp_predict, src/singlet.cpp:350-367) for every padded-rank code path, with
+    empty columns, L1 and L2."""
+    from singlet_b200 import api, synth
+
+    m, n = 700, 450
+    A, At = _mk(m, n, 0.08, seed=k, empty_cols=(0, 17, n - 1))
+    w = synth.w_init(k, m, seed=k + 1)
+    for L1, L2 in ((0.0, 0.0), (0.01, 0.0), (0.05, 0.1)):
+        dev = api.Rcpp_predict(A, w, L1, L2, 0)
+        ref = oracle.predict(A, w, np.zeros((k, n)), L1, L2)
+        assert np.all(dev[:, [0, 17, n - 1]] == 0)
+        scale = np.abs(ref).max()
+        assert np.abs(dev - ref).max() <= 2e-4 * scale, (k, L1, L2, np.abs(dev - ref).max() / scale)
+
+
+@pytest.mark.parametrize("k,maxit", [(4, 12), (10, 10), (32, 8), (48, 5)])
+def test_nmf_matches_oracle(handle, oracle, k, maxit):
+    """c_nmf (src/singlet.cpp:638-672) at a fixed iteration count."""
+    from singlet_b200 import api, synth
+
+    m, n = 900, 600
+    A, At = _mk(m, n, 0.06, seed=100 + k)
+    w0 = synth.w_init(k, m, seed=k)
+    dev = api.c_nmf(A, At, 0.0, maxit, False, 0.01, 0.02, 0.0, 0.0, 0, w0)
+    ref = oracle.nmf(A, At, w0, tol=0.0, maxit=maxit, L1=(0.01, 0.02), L2=(0.0, 0.0))
+    assert dev["iter"] == ref["iter"] == maxit
+    perm = match_factors(ref["w"], dev["w"])
+    assert min_factor_cor(ref["w"], dev["w"], perm) >= COR_MIN
+    assert min_factor_cor(ref["h"], dev["h"], perm) >= COR_MIN
+    assert np.allclose(dev["d"][perm], ref["d"], rtol=5e-3)
+    assert abs(dev["tol"] - ref["tol"][-1]) <= 1e-3 * max(ref["tol"][-1], 1e-6) + 1e-7
+    tr_dev = oracle.mse_train(A, dev["w"], dev["d"], dev["h"])
+    tr_ref = oracle.mse_train(A, ref["w"], ref["d"], ref["h"])
+    assert abs(tr_dev - tr_ref) <= MSE_RTOL * tr_ref
+
+
+def test_nmf_tol_stop_and_callbacks(handle, oracle, capsys):
+    """Stops on tol like the reference loop condition (src/singlet.cpp:647) and prints its table."""
+    from singlet_b200 import api, synth
+
+    m, n, k = 800, 500, 6
+    A, At = _mk(m, n, 0.07, seed=5)
+    w0 = synth.w_init(k, m, seed=2)
+    dev = api.c_nmf(A, At, 1e-3, 100, True, 0.01, 0.01, 0.0, 0.0, 0, w0)
+    ref = oracle.nmf(A, At, w0, tol=1e-3, maxit=100)
+    assert abs(dev["iter"] - ref["iter"]) <= 1
+    out = capsys.readouterr().out
+    assert "iter |      tol" in out and ("%4d | " % dev["iter"]) in out
+    z = api.c_nmf(A, At, 1e-3, 0, False, 0.01, 0.01, 0.0, 0.0, 0, w0)  # maxit = 0 -> h = 0 (App. A-2)
+    assert z["iter"] == 0 and np.all(z["h"] == 0) and np.allclose(z["w"], w0, rtol=1e-6)
+
+
+def test_mask_lists_bit_exact(oracle):
+    """Held-out index lists of both orientations equal rng::draw of the reference, entry by entry."""
+    from singlet_b200.sharded import CudaBackend
+
+    m, n = 913, 420
+    A, At = _mk(m, n, 0.06, seed=9)
+    be = CudaBackend(0)
+    try:
+        hA, hAt = be.upload(A), be.upload(At)
+        for seed, inv in ((123, 20), (999, 7), (2**40 + 17, 70000)):
+            mA = be.mask_build(hA, seed, inv, 0, 0, 0)
+            mAt = be.mask_build(hAt, seed, inv, 1, 0, 0)
+            full = np.array([oracle.mask_cell(seed, c, m, inv) for c in range(n)], dtype=bool)  # [cell][gene]
+            buf = np.zeros(max(m, n), np.int32)
+            tot = 0
+            for c in range(n):
+                cnt = be.lib.sgl_mask_column(be._h, mA, c, buf.ctypes.data, buf.size)
+                assert np.array_equal(buf[:cnt], np.nonzero(full[c])[0])
+                tot += cnt
+            for g in range(0, m, 7):
+                cnt = be.lib.sgl_mask_column(be._h, mAt, g, buf.ctypes.data, buf.size)
+                assert np.array_equal(buf[:cnt], np.nonzero(full[:, g])[0])
+            a, b = C.c_int64(), C.c_int64()
+            be.lib.sgl_mask_info(mA, C.byref(a), C.byref(b))
+            assert a.value == tot == int(full.sum())
+            held_nz = int(sum(full[c, A.indices[A.indptr[c]:A.indptr[c + 1]]].sum() for c in range(n)))
+            assert b.value == held_nz
+    finally:
+        be.close()
+
+
+@pytest.mark.parametrize("k,maxit,trace", [(3, 9, 2), (10, 8, 3), (32, 5, 5), (40, 4, 1)])
+def test_ard_nmf_matches_oracle(handle, oracle, k, maxit, trace):
+    """c_ard_nmf (src/singlet.cpp:1090-1159): trace indices identical, test MSE within 1e-4."""
+    from singlet_b200 import api, synth
+
+    m, n = 700, 520
+    A, At = _mk(m, n, 0.08, seed=40 + k, empty_cols=(5,))
+    w0 = synth.w_init(k, m, seed=k)
+    dev = api.c_ard_nmf(A, At, 0.0, maxit, False, 0.01, 0.0, 0, w0, 123, 20, 10.0, trace)
+    ref = oracle.ard_nmf(A, At, w0, 123, 20, tol=0.0, maxit=maxit, L1=0.01, L2=0.0, overfit_threshold=10.0,
+                         trace_test_mse=trace)
+    assert list(dev["iter"]) == list(ref["iter"])
+    assert np.allclose(dev["test_mse"], ref["test_mse"], rtol=MSE_RTOL)
+    assert np.allclose(dev["score_overfit"], ref["score_overfit"], atol=1e-4)
+    perm = match_factors(ref["w"], dev["w"])
+    assert min_factor_cor(ref["w"], dev["w"], perm) >= COR_MIN
+    assert min_factor_cor(ref["h"], dev["h"], perm) >= COR_MIN
+    tr_dev = oracle.mse_train(A, dev["w"], dev["d"], dev["h"], 123, 20)
+    tr_ref = oracle.mse_train(A, ref["w"], ref["d"], ref["h"], 123, 20)
+    assert abs(tr_dev - tr_ref) <= MSE_RTOL * tr_ref
+
+
+def test_ard_overfit_break(handle, oracle):
+    """The early `break` on score_overfit > threshold leaves iter_ un-incremented (App. A-13)."""
+    from singlet_b200 import api, synth
+
+    m, n, k = 500, 300, 6
+    A, At = _mk(m, n, 0.07, seed=3)
+    w0 = synth.w_init(k, m, seed=5)
+    dev = api.c_ard_nmf(A, At, 1e-4, 12, False, 0.01, 0.0, 0, w0, 123, 20, 1e-4, 3)
+    ref = oracle.ard_nmf(A, At, w0, 123, 20, tol=1e-4, maxit=12, trace_test_mse=3)
+    assert list(dev["iter"]) == list(ref["iter"])
+    assert np.allclose(dev["test_mse"], ref["test_mse"], rtol=MSE_RTOL)
+
+
+def test_project_model_matches_oracle(handle, oracle):
+    """c_project_model (src/singlet.cpp:405-413) with w given as m x k (transposed inside) or k x m."""
+    from singlet_b200 import api, synth
+
+    m, n, k = 650, 380, 12
+    A, At = _mk(m, n, 0.07, seed=77)
+    w = synth.w_init(k, m, seed=1)
+    ref = oracle.project_model(A, w)
+    for arg in (w, np.ascontiguousarray(w.T)):
+        dev = api.project_model(A, arg)
+        assert min_factor_cor(ref["h"], dev["h"]) >= COR_MIN
+        assert np.allclose(dev["d"], ref["d"], rtol=5e-3)
+    with pytest.raises(ValueError):
+        api.project_model(A, np.ones((k, m + 1)))
+
+
+def test_chunked_lists_match_single(handle, oracle):
+    """c_nmf_sparse_list / c_ard_nmf_sparse_list (src/singlet.cpp:715-743, 1162-1234): a column-chunk list
+    plus gene-block transposes gives the same model as the single matrix (global hash indices)."""
+    from singlet_b200 import api, synth
+
+    m, n, k = 600, 410, 5
+    A, At = _mk(m, n, 0.07, seed=21)
+    Al = [A[:, :100].tocsc(), A[:, 100:101].tocsc(), A[:, 101:].tocsc()]
+    Atl = api._distributed_transpose(Al)
+    assert sum(a.shape[1] for a in Atl) == m
+    w0 = synth.w_init(k, m, seed=4)
+    one = api.c_nmf(A, At, 0.0, 6, False, 0.01, 0.01, 0, 0, 0, w0)
+    lst = api.c_nmf_sparse_list(Al, Atl, 0.0, 6, False, 0.01, 0, 0, w0)
+    assert np.array_equal(one["w"], lst["w"]) and np.array_equal(one["h"], lst["h"])
+    one = api.c_ard_nmf(A, At, 0.0, 4, False, 0.01, 0, 0, w0, 999, 20, 10.0, 2)
+    lst = api.c_ard_nmf_sparse_list(Al, Atl, 0.0, 4, False, 0.01, 0, 0, w0, 999, 20, 10.0, 2)
+    assert np.array_equal(one["test_mse"], lst["test_mse"]) and np.array_equal(one["h"], lst["h"])
+    ref = oracle.ard_nmf(Al, Atl, w0, 999, 20, tol=0.0, maxit=4, overfit_threshold=10.0, trace_test_mse=2)
+    assert np.allclose(lst["test_mse"], ref["test_mse"], rtol=MSE_RTOL)
+
+
+def test_error_paths(handle):
+    from singlet_b200 import SingletCudaError, api, synth
+
+    A, At = _mk(300, 200, 0.05, seed=1)
+    with pytest.raises(SingletCudaError):  # rank above SGL_MAX_RANK
+        api.c_nmf(A, At, 1e-4, 2, False, 0, 0, 0, 0, 0, np.ones((129, 300)))
+    with pytest.raises(SingletCudaError):  # At is not transpose-shaped
+        api.c_nmf(A, A, 1e-4, 2, False, 0, 0, 0, 0, 0, synth.w_init(4, 300))
+    with pytest.raises(SingletCudaError):  # trace_test_mse = 0 divides by zero in the reference
+        api.c_ard_nmf(A, At, 1e-4, 2, False, 0, 0, 0, synth.w_init(4, 300), 1, 20, 1e-3, 0)
