@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -357,9 +358,10 @@ static int launch_spmm(sgl_handle* h, const sgl_matrix* X, const uint2* rec, con
         SGL_CUDA(cudaFuncSetAttribute(spmm_tiles_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
+    static const int dbg = getenv("SGL_SPMM_DEBUG") ? atoi(getenv("SGL_SPMM_DEBUG")) : 0;
     dim3 grid(blocks_for(X->ncol, C::COLS_PER_CTA), (unsigned)splits);
     spmm_tiles_kernel<KP><<<grid, C::WARPS * 32, smem, h->stream>>>(rec, X->colptr, ti.tileptr, X->ncol, ti.ncol_pad, X->nrow,
-                                                                   ti.rb_rows, ti.n_tiles, tiles_per_split, F, Bout);
+                                                                   ti.rb_rows, ti.n_tiles, tiles_per_split, F, Bout, dbg);
     LAUNCH_CHECK(h);
     return SGL_OK;
 }

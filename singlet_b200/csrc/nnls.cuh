@@ -48,7 +48,7 @@ __device__ __forceinline__ float cd_step(float bi, float inv_aii, float& xi, flo
 template <int KP>
 struct NnlsCfg {
     static constexpr int THREADS = (KP <= 32) ? 128 : 64;
-    static constexpr int MIN_CTAS = (KP <= 32) ? 4 : 3;  // register cap: 128 (KP<=32) / 170 (KP=64)
+    static constexpr int MIN_CTAS = (KP <= 32) ? 3 : 2;  // register cap: 128 (KP<=32) / 170 (KP=64)
 };
 
 // branch-free coordinate step (same arithmetic as cd_step): returns MINUS the delta, i.e. the

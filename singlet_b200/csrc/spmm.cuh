@@ -42,7 +42,10 @@ static inline int spmm_tile_rows(int kp) {
     const int budget = (227 * 1024 - 1024) / 2;  // bytes per stage
     int rows = budget / (kp * 4);
     rows &= ~7;
-    return rows;
+    // 800 rows at KP = 32: at 5 % density a (column, tile) sub-range then averages 40 records, so
+    // one group of UNR * SLOTS = 48 record loads covers ~90 % of the sub-ranges in a single pass
+    const int cap = 800 * 32 / kp;
+    return rows < cap ? rows : cap;
 }
 
 // packed FP32 pair FMA (sm_100 FFMA2; SASS takes the scalar operand as a broadcast .F32):
@@ -62,7 +65,8 @@ spmm_tiles_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ col
                   const int32_t* __restrict__ tileptr,  // [n_tiles + 1][ncol_pad]
                   int64_t ncol, int64_t ncol_pad, int64_t nrow, int rb_rows, int n_tiles, int tiles_per_split,
                   const float* __restrict__ F,  // [nrow][KP]
-                  float* __restrict__ Bout)     // [splits][ncol][KP]
+                  float* __restrict__ Bout,     // [splits][ncol][KP]
+                  int dbg)                      // debug knobs (SGL_SPMM_DEBUG): 1 = no L2 prefetch, 2 = fake records
 {
     using C = SpmmCfg<KP>;
     constexpr int UNR = C::UNR;
@@ -133,7 +137,7 @@ spmm_tiles_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ col
         int32_t p3 = p2;
         if (my_col_ok) {
             if (t + 2 < t_end) p3 = tileptr[(int64_t)(t + 3) * ncol_pad + my_col];
-            if (t + 1 < t_end) l2_prefetch_records(rec + my_base + p1, p2 - p1);
+            if (t + 1 < t_end && !(dbg & 1)) l2_prefetch_records(rec + my_base + p1, p2 - p1);
         }
         mbar_wait(&bars[s], s ? phase1 : phase0);
         if (s) phase1 ^= 1u; else phase0 ^= 1u;
@@ -153,9 +157,10 @@ spmm_tiles_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ col
                 uint2 r[UNR];
 #pragma unroll
                 for (int u = 0; u < UNR; ++u)
-                    r[u] = (rem > u * C::SLOTS) ? ldg_stream_u2(lp + u * C::SLOTS) : make_uint2(pad_row, 0u);
+                    r[u] = (rem > u * C::SLOTS) ? ((dbg & 2) ? make_uint2(pad_row + (uint32_t)((rem * 37 + u * 11) & 511), 0x3f800000u) : ldg_stream_u2(lp + u * C::SLOTS)) : make_uint2(pad_row, 0u);
 #pragma unroll
                 for (int u = 0; u < UNR; ++u) {
+                    if (done + u * C::SLOTS >= n) break;  // warp-uniform: no step past the sub-range
                     const float v = __uint_as_float(r[u].y);
                     const uint32_t a = tile_q + r[u].x * (uint32_t)(KP * 4);
 #pragma unroll
