@@ -55,10 +55,12 @@ struct DevBuf {  // grow-only device scratch
     }
 };
 
-struct TileIndex {
-    int rb_rows = 0, n_tiles = 0;
-    int64_t ncol_pad = 0;
+struct TileIndex {  // per padded rank: row tiling + the matrix re-laid out as warp streams (spmm.cuh)
+    int rb_rows = 0, n_tiles = 0, nc = 0, pad = 0;
+    int64_t ncol_pad = 0, n_groups = 0, stream_len = 0;
     int32_t* tileptr = nullptr;
+    int64_t* goff = nullptr;
+    uint2* stream = nullptr;
 };
 
 }  // namespace sgl
@@ -79,6 +81,7 @@ struct sgl_mask {
     int mask_t = 0;
     int64_t col_offset = 0, row_offset = 0;
     uint2* rec_train = nullptr;  // copy of X->rec with held-out values zeroed
+    std::map<int, uint2*> stream_train;  // its warp streams, per padded rank (lazily built)
     int64_t* mptr = nullptr;     // ncol + 1
     uint2* mrec = nullptr;       // held-out {row, value bits}
     int64_t n_masked = 0, n_masked_nz = 0;
@@ -173,13 +176,18 @@ static void matrix_release(sgl_matrix* m) {
     if (!m) return;
     if (m->colptr) cudaFree(m->colptr);
     if (m->rec) cudaFree(m->rec);
-    for (auto& kv : m->tiles)
+    for (auto& kv : m->tiles) {
         if (kv.second.tileptr) cudaFree(kv.second.tileptr);
+        if (kv.second.goff) cudaFree(kv.second.goff);
+        if (kv.second.stream) cudaFree(kv.second.stream);
+    }
     delete m;
 }
 static void mask_release(sgl_mask* m) {
     if (!m) return;
     if (m->rec_train) cudaFree(m->rec_train);
+    for (auto& kv : m->stream_train)
+        if (kv.second) cudaFree(kv.second);
     if (m->mptr) cudaFree(m->mptr);
     if (m->mrec) cudaFree(m->mrec);
     delete m;
@@ -287,6 +295,21 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
     return SGL_OK;
 }
 
+// re-lay `rec` (column-compressed, same structure as m->rec) out as warp streams for tile index ti
+static int build_stream(sgl_handle* h, const sgl_matrix* m, const TileIndex& ti, const uint2* rec, uint2** out) {
+    uint2* st = nullptr;
+    // one CHUNK of slack: the kernel's last cp.async chunk of a stream may start inside the array only
+    SGL_CUDA(cudaMalloc(&st, sizeof(uint2) * (size_t)(ti.stream_len + 64)));
+    const int64_t warps = ti.n_groups * ti.n_tiles;
+    if (warps > 0) {
+        stream_fill_kernel<<<blocks_for(warps, 8), 256, 0, h->stream>>>(rec, m->colptr, ti.tileptr, ti.goff, m->ncol, ti.ncol_pad,
+                                                                     ti.n_tiles, ti.rb_rows, ti.nc, ti.pad, ti.n_groups, st);
+        LAUNCH_CHECK(h);
+    }
+    *out = st;
+    return SGL_OK;
+}
+
 // tile index for padded rank KP (lazily built, cached on the matrix)
 static int get_tiles(sgl_handle* h, sgl_matrix* m, int kpv, const TileIndex** out) {
     auto it = m->tiles.find(kpv);
@@ -315,8 +338,24 @@ static int get_tiles(sgl_handle* h, sgl_matrix* m, int kpv, const TileIndex** ou
     dim3 grid(blocks_for(ti.ncol_pad, 256), (unsigned)(ti.n_tiles + 1));
     build_tileptr_kernel<<<grid, 256, 0, h->stream>>>(m->rec, m->colptr, m->ncol, ti.ncol_pad, ti.rb_rows, ti.n_tiles, ti.tileptr);
     LAUNCH_CHECK(h);
+    // warp-stream layout: group offsets by count + exclusive scan, then one copy pass
+    DISPATCH_KP(kpv, (ti.nc = SpmmCfg<KP>::NC, ti.pad = SpmmCfg<KP>::PAD));
+    ti.n_groups = (m->ncol + ti.nc - 1) / ti.nc;
+    if (ti.n_groups < 1) ti.n_groups = 1;
+    const int64_t n_off = ti.n_groups * (ti.n_tiles + 1);
+    SGL_TRY(h->counts.ensure((size_t)n_off + 2));
+    SGL_CUDA(cudaMalloc(&ti.goff, sizeof(int64_t) * (size_t)(n_off + 1)));
+    stream_counts_kernel<<<blocks_for(n_off, 256), 256, 0, h->stream>>>(ti.tileptr, m->ncol, ti.ncol_pad, ti.n_tiles, ti.nc, ti.pad,
+                                                                      ti.n_groups, h->counts.p);
+    LAUNCH_CHECK(h);
+    exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->counts.p, n_off, ti.goff);
+    LAUNCH_CHECK(h);
+    SGL_CUDA(cudaMemcpyAsync(&ti.stream_len, ti.goff + n_off, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    SGL_CUDA(cudaStreamSynchronize(h->stream));
     m->tiles[kpv] = ti;
-    *out = &m->tiles[kpv];
+    TileIndex& ref = m->tiles[kpv];
+    SGL_TRY(build_stream(h, m, ref, m->rec, &ref.stream));
+    *out = &ref;
     return SGL_OK;
 }
 
@@ -349,19 +388,18 @@ static int dev_gram(sgl_handle* h, const float* F, int k, int64_t cols, double* 
 }
 
 template <int KP>
-static int launch_spmm(sgl_handle* h, const sgl_matrix* X, const uint2* rec, const TileIndex& ti, const float* F,
+static int launch_spmm(sgl_handle* h, const sgl_matrix* X, const uint2* stream, const TileIndex& ti, const float* F,
                        float* Bout, int splits, int tiles_per_split) {
     using C = SpmmCfg<KP>;
-    const size_t smem = 2 * (size_t)ti.rb_rows * KP * sizeof(float) + 2 * sizeof(uint64_t);
+    const size_t smem = 2 * (size_t)ti.rb_rows * KP * sizeof(float) + C::RING_BYTES + 2 * sizeof(uint64_t);
     static bool attr_done = false;
     if (!attr_done) {
-        SGL_CUDA(cudaFuncSetAttribute(spmm_tiles_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SGL_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    static const int dbg = getenv("SGL_SPMM_DEBUG") ? atoi(getenv("SGL_SPMM_DEBUG")) : 0;
-    dim3 grid(blocks_for(X->ncol, C::COLS_PER_CTA), (unsigned)splits);
-    spmm_tiles_kernel<KP><<<grid, C::WARPS * 32, smem, h->stream>>>(rec, X->colptr, ti.tileptr, X->ncol, ti.ncol_pad, X->nrow,
-                                                                   ti.rb_rows, ti.n_tiles, tiles_per_split, F, Bout, dbg);
+    dim3 grid(blocks_for(ti.n_groups, C::WARPS), (unsigned)splits);
+    spmm_stream_kernel<KP><<<grid, C::WARPS * 32, smem, h->stream>>>(stream, ti.goff, ti.tileptr, X->ncol, ti.ncol_pad, X->nrow,
+                                                                    ti.rb_rows, ti.n_tiles, tiles_per_split, F, Bout);
     LAUNCH_CHECK(h);
     return SGL_OK;
 }
@@ -397,7 +435,19 @@ static int dev_update(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask,
     const int tiles_per_split = (ti->n_tiles + splits - 1) / splits;
     splits = (ti->n_tiles + tiles_per_split - 1) / tiles_per_split;
     SGL_TRY(h->bparts.ensure((size_t)splits * (size_t)X->ncol * KPV));
-    const uint2* rec = mask ? mask->rec_train : X->rec;
+    const uint2* rec = ti->stream;
+    if (mask) {  // training copy of the stream (held-out values zeroed), built once per padded rank
+        sgl_mask* mm = const_cast<sgl_mask*>(mask);
+        auto it = mm->stream_train.find(KPV);
+        if (it == mm->stream_train.end()) {
+            uint2* st = nullptr;
+            SGL_TRY(build_stream(h, X, *ti, mask->rec_train, &st));
+            mm->stream_train[KPV] = st;
+            rec = st;
+        } else {
+            rec = it->second;
+        }
+    }
     {
         // algorithmic bytes of this launch: 8*nnz + 4*(ncol+1) + 4*k*nrow + 4*k*ncol
         ProfScope ps(h, PK_SPMM, 8 * X->nnz + 4 * (X->ncol + 1) + 4ll * k * X->nrow + 4ll * k * X->ncol);

@@ -1,23 +1,28 @@
 // spmm.cuh -- sparse right-hand-side product  B[:, c] = sum_{nz (r, v) in X[:, c]} v * F[r, :]
 // (the `b += it.value() * w.col(it.row())` loop of predict, reference src/singlet.cpp:341-343).
 //
-// Layout. X is column-compressed with 8-byte records {int32 row, float value}; the gather operand F
-// is float [rows][KP]. F does not fit in shared memory (k x m = 3.84 MB, k x n = 128 MB at the
-// headline config), so rows are cut into tiles of `rb_rows` rows; a precomputed table
-// tileptr[t][col] gives, for every column, where tile t starts inside the column's record range
-// (rows are ascending within a column, so every (column, tile) sub-range is contiguous).
+// HBM layout ("warp streams"). The gather operand F (float [rows][KP]) does not fit in shared memory
+// (k x m = 3.84 MB, k x n = 128 MB at the headline config), so rows are cut into tiles of rb_rows
+// rows that are staged through shared memory, and the non-zeros are stored IN THE ORDER THE KERNEL
+// CONSUMES THEM: columns are grouped NC at a time (one group = one warp); the stream of a group is
+//     for tile t: for column j of the group: the records {int32 row, float value} of X[:, col] whose
+//     row falls in tile t, padded with {first row of tile t, 0.0f} to a multiple of PAD records.
+// goff[group][t] is the stream position of (group, t). A warp therefore reads ONE contiguous array
+// front to back: fully coalesced, no per-record predicates, and trivially prefetchable.
 //
-// One CTA owns WARPS*NC columns and walks a range of row tiles. Per tile the F tile
-// (rb_rows x KP floats, contiguous in memory) is staged into shared memory by ONE bulk async copy
-// (TMA, cp.async.bulk -> SASS UBLKCP) into a 2-deep ring guarded by mbarriers, so the load of tile
-// t+1 overlaps the FMAs of tile t. Each warp keeps the accumulators of its NC columns in registers
-// for the whole walk: LPN = min(8, KP/4) lanes cooperate on one non-zero (each lane owns FPL = KP/LPN
-// factors as float4s), so one LDS.128 per lane fetches 32/LPN gathered rows with every 8-lane
-// phase reading one contiguous 128-byte row (bank-conflict free), and the record {row, value} is
-// fetched once per lane group straight from the HBM stream (read-once, L1 no-allocate).
+// Kernel. One CTA = 16 warps = 16 column groups; it walks a range of row tiles. Per tile the F tile
+// (rb_rows x KP floats, contiguous) is staged by ONE bulk async copy (TMA: cp.async.bulk -> UBLKCP)
+// into a 2-deep ring guarded by mbarriers, so the load of tile t+1 overlaps the FMAs of tile t. Each
+// warp keeps a private ring of RC chunks (64 records each) in shared memory that it fills with
+// cp.async (LDGSTS) RC-1 chunks ahead of its read position -- the HBM latency of the record stream
+// never reaches the math -- and keeps the accumulators of its NC columns in registers for the whole
+// walk. LPN = min(8, KP/4) lanes cooperate on one non-zero (each lane owns FPL = KP/LPN factors as
+// 16-byte chunks), so one LDS.128 fetches 32/LPN gathered rows with every 8-lane phase reading one
+// contiguous 128-byte row (bank-conflict free); products run on packed FFMA2.
 //
-// Roofline note: the HBM stream is 8 B per non-zero, the shared-memory gather is
-// KP*4 B per non-zero; at KP = 32 the 128 B/clk/SM crossbar caps the kernel at ~1 non-zero/clk/SM.
+// Roofline note: HBM sees 8 B per non-zero (+ padding), the shared-memory crossbar sees
+// KP*4 B of gather per non-zero; at KP = 32 the 128 B/clk/SM crossbar caps the kernel at about one
+// non-zero per clock per SM.
 #pragma once
 #include "common.cuh"
 
@@ -27,62 +32,80 @@ template <int KP>
 struct SpmmCfg {
     static constexpr int LPN = (KP / 4 < 8) ? (KP / 4) : 8;  // lanes per non-zero
     static constexpr int FPL = KP / LPN;                     // factors per lane (4, 8 or 16)
-    static constexpr int NV = FPL / 4;                       // 16-byte loads per lane per non-zero
+    static constexpr int NV = FPL / 4;                       // 16-byte gathers per lane per non-zero
     static constexpr int SLOTS = 32 / LPN;                   // non-zeros per warp step
     static constexpr int NC = (64 / FPL);                    // columns per warp (64 accumulator regs)
     static constexpr int WARPS = 16;
     static constexpr int COLS_PER_CTA = WARPS * NC;
-    // record loads issued back to back before the first use: one group covers ~48 non-zeros, i.e. a
-    // typical (column, tile) sub-range, so each sub-range exposes one memory latency
-    static constexpr int UNR = (48 / SLOTS) < 2 ? 2 : (48 / SLOTS);
+    static constexpr int DS = (KP <= 32) ? 2 : 1;            // warp steps per record fetch (LDS.128 / LDS.64)
+    static constexpr int PAD = DS * SLOTS;                   // sub-ranges are padded to this many records
+    static constexpr int CHUNK = 64;                         // records per cp.async chunk (512 B)
+    static constexpr int RC = 4;                             // ring chunks per warp (2 KB)
+    static constexpr int RING_BYTES = WARPS * RC * CHUNK * 8;
 };
+constexpr int SPMM_RING_BYTES = 16 * 4 * 64 * 8;
 
-// rows per staged tile: two stages must fit in 227 KB of shared memory
+// rows per staged F tile: two stages + the record rings must fit in 227 KB of shared memory
 static inline int spmm_tile_rows(int kp) {
-    const int budget = (227 * 1024 - 1024) / 2;  // bytes per stage
+    const int budget = (227 * 1024 - 1024 - SPMM_RING_BYTES) / 2;  // bytes per stage
     int rows = budget / (kp * 4);
     rows &= ~7;
-    // 800 rows at KP = 32: at 5 % density a (column, tile) sub-range then averages 40 records, so
-    // one group of UNR * SLOTS = 48 record loads covers ~90 % of the sub-ranges in a single pass
-    const int cap = 800 * 32 / kp;
-    return rows < cap ? rows : cap;
+    return rows;
 }
 
-// packed FP32 pair FMA (sm_100 FFMA2; SASS takes the scalar operand as a broadcast .F32):
-//   acc.{lo,hi} += w.{lo,hi} * v
 __device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long w, float v) {
-    unsigned long long vv;
+    unsigned long long vv;  // SASS: FFMA2 takes the scalar as a broadcast .F32 operand, no move needed
     asm("mov.b64 %0, {%1, %1};" : "=l"(vv) : "f"(v));
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(vv));
 }
 __device__ __forceinline__ void lds_2x64(uint32_t addr, unsigned long long& a, unsigned long long& b) {
-    asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+// 16-byte async copy global -> shared (LDGSTS), bypassing L1; src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 template <int KP>
 __global__ void __launch_bounds__(SpmmCfg<KP>::WARPS * 32, 1)
-spmm_tiles_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ colptr,
-                  const int32_t* __restrict__ tileptr,  // [n_tiles + 1][ncol_pad]
-                  int64_t ncol, int64_t ncol_pad, int64_t nrow, int rb_rows, int n_tiles, int tiles_per_split,
-                  const float* __restrict__ F,  // [nrow][KP]
-                  float* __restrict__ Bout,     // [splits][ncol][KP]
-                  int dbg)                      // debug knobs (SGL_SPMM_DEBUG): 1 = no L2 prefetch, 2 = fake records
+spmm_stream_kernel(const uint2* __restrict__ stream,     // warp streams (see header)
+                   const int64_t* __restrict__ goff,     // [n_groups][n_tiles + 1]
+                   const int32_t* __restrict__ tileptr,  // [n_tiles + 1][ncol_pad]
+                   int64_t ncol, int64_t ncol_pad, int64_t nrow, int rb_rows, int n_tiles, int tiles_per_split,
+                   const float* __restrict__ F,  // [nrow][KP]
+                   float* __restrict__ Bout)     // [splits][ncol][KP]
 {
     using C = SpmmCfg<KP>;
-    constexpr int UNR = C::UNR;
-    constexpr int GROUP = UNR * C::SLOTS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage0 = reinterpret_cast<float*>(smem_raw);
     const size_t stage_floats = (size_t)rb_rows * KP;
     float* stage1 = stage0 + stage_floats;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage1 + stage_floats);  // 2 "full" barriers
+    unsigned char* ring_all = reinterpret_cast<unsigned char*>(stage1 + stage_floats);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring_all + C::RING_BYTES);  // 2 "full" barriers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = lane % C::LPN;  // factor chunk owned by this lane
     const int g = lane / C::LPN;  // non-zero slot inside a warp step
-    const int64_t col0 = (int64_t)blockIdx.x * C::COLS_PER_CTA + (int64_t)warp * C::NC;
+    const int64_t group = (int64_t)blockIdx.x * C::WARPS + warp;
+    const int64_t col0 = group * C::NC;
     const int t_begin = blockIdx.y * tiles_per_split;
     const int t_end = min(n_tiles, t_begin + tiles_per_split);
+    const bool group_ok = col0 < ncol;
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
@@ -91,7 +114,7 @@ spmm_tiles_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ col
     }
     __syncthreads();
 
-    auto issue = [&](int t) {  // thread 0 only
+    auto issue = [&](int t) {  // thread 0 only: stage F tile t
         const int s = (t - t_begin) & 1;
         const int64_t r0 = (int64_t)t * rb_rows;
         const int64_t rows = min((int64_t)rb_rows, nrow - r0);
@@ -104,6 +127,28 @@ spmm_tiles_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ col
         if (t_begin + 1 < t_end) issue(t_begin + 1);
     }
 
+    // ---- this warp's record stream and ring ----
+    int64_t s_begin = 0, s_total = 0;
+    if (group_ok && t_begin < t_end) {
+        s_begin = goff[group * (n_tiles + 1) + t_begin];
+        s_total = goff[group * (n_tiles + 1) + t_end] - s_begin;  // records, multiple of PAD
+    }
+    const uint2* sp = stream + s_begin;
+    const int64_t n_chunks = (s_total + C::CHUNK - 1) / C::CHUNK;
+    const uint32_t ring = smem_u32(ring_all) + (uint32_t)warp * (C::RC * C::CHUNK * 8);
+    auto fill = [&](int64_t c) {  // whole warp: chunk c -> ring slot c % RC (2 records per lane)
+        if (c < n_chunks) {
+            const int64_t r = c * C::CHUNK + 2 * lane;
+            const bool in = r < s_total;  // s_total and r are even: a lane's pair is in or out as a whole
+            cp_async16(ring + (uint32_t)((c % C::RC) * C::CHUNK + 2 * lane) * 8u, sp + (in ? r : 0), in ? 16u : 0u);
+        }
+        cp_async_commit();  // always commit so that the group count stays uniform
+    };
+#pragma unroll
+    for (int c = 0; c < C::RC; ++c) fill(c);
+    cp_async_wait<C::RC - 1>();  // chunk 0 has landed
+    __syncwarp();
+
     // accumulators: NC columns x FPL factors, as packed FP32 pairs
     unsigned long long acc[C::NC][C::FPL / 2];
 #pragma unroll
@@ -111,74 +156,72 @@ spmm_tiles_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ col
 #pragma unroll
         for (int f = 0; f < C::FPL / 2; ++f) acc[j][f] = 0ull;
 
-    // this lane's column (for the coalesced tile-pointer loads) and its record base
+    // per-column record counts of a tile come from the tile index (lanes < NC hold one column each)
     const int64_t my_col = col0 + lane;
     const bool my_col_ok = (lane < C::NC) && (my_col < ncol);
-    const int64_t my_base = my_col_ok ? colptr[my_col] : 0;
-
-    // tileptr[t][col] is both the end of tile t-1 and the start of tile t. Each lane (< NC) keeps the
-    // boundaries of its column three tiles deep so that, at the top of tile t, it can (a) fetch the
-    // boundary needed two tiles later and (b) ask L2 to prefetch the column's records of tile t+1
-    // with one bulk prefetch (the record loads of the next tile then hit L2 instead of HBM).
-    int32_t p0 = 0, p1 = 0, p2 = 0;  // tileptr[t], tileptr[t+1], tileptr[t+2]
+    int32_t p0 = 0, p1 = 0;  // tileptr[t], tileptr[t+1]
     if (my_col_ok && t_begin < t_end) {
         p0 = tileptr[(int64_t)t_begin * ncol_pad + my_col];
         p1 = tileptr[(int64_t)(t_begin + 1) * ncol_pad + my_col];
-        p2 = (t_begin + 1 < t_end) ? tileptr[(int64_t)(t_begin + 2) * ncol_pad + my_col] : p1;
-        l2_prefetch_records(rec + my_base + p0, p1 - p0);
     }
 
+    uint32_t pos = 0;  // records consumed so far (multiple of PAD); ring offset = pos % (RC*CHUNK)
     uint32_t phase0 = 0, phase1 = 0;
     for (int t = t_begin; t < t_end; ++t) {
         const int s = (t - t_begin) & 1;
-        // per-lane (lanes < NC): first record of this column in tile t, and how many
-        const int64_t start_l = my_base + p0;
-        const int32_t cnt_l = p1 - p0;
-        int32_t p3 = p2;
-        if (my_col_ok) {
-            if (t + 2 < t_end) p3 = tileptr[(int64_t)(t + 3) * ncol_pad + my_col];
-            if (t + 1 < t_end && !(dbg & 1)) l2_prefetch_records(rec + my_base + p1, p2 - p1);
-        }
+        const int32_t steps_l = (p1 - p0 + C::PAD - 1) / C::PAD;  // fetch steps of my column in this tile
+        int32_t p2 = p1;
+        if (my_col_ok && t + 1 < t_end) p2 = tileptr[(int64_t)(t + 2) * ncol_pad + my_col];
         mbar_wait(&bars[s], s ? phase1 : phase0);
         if (s) phase1 ^= 1u; else phase0 ^= 1u;
         // shared address of (row 0 of the matrix, chunk q) as seen through this tile: adding
         // row * KP * 4 for any row of the tile lands inside the stage (32-bit wrap-around is fine)
         const uint32_t tile_q = smem_u32(s ? stage1 : stage0) + (uint32_t)q * 16u - (uint32_t)(t * rb_rows) * (uint32_t)(KP * 4);
 
-        const uint32_t pad_row = (uint32_t)(t * rb_rows);  // a valid row of this tile
 #pragma unroll
         for (int j = 0; j < C::NC; ++j) {
-            const int64_t start = __shfl_sync(0xffffffffu, start_l, j);
-            const int32_t n = __shfl_sync(0xffffffffu, cnt_l, j);
-            const uint2* lp = rec + start + g;  // this lane's first record
-            int32_t rem = n - g;                // records left for this lane's slot (may be <= 0)
-            for (int32_t done = 0; done < n; done += GROUP) {  // warp-uniform
-                // slots past the end of the sub-range gather a valid row with value 0 (adds +0)
-                uint2 r[UNR];
+            const int32_t steps = __shfl_sync(0xffffffffu, steps_l, j);
+            for (int32_t st = 0; st < steps; ++st) {  // warp-uniform
+                const uint32_t roff = ring + ((pos & (C::RC * C::CHUNK - 1)) + (uint32_t)(C::DS * g)) * 8u;
+                if constexpr (C::DS == 2) {
+                    const uint4 rr = lds_u4(roff);  // two records {row0, val0, row1, val1}
+                    const uint32_t a0 = tile_q + rr.x * (uint32_t)(KP * 4);
+                    const uint32_t a1 = tile_q + rr.z * (uint32_t)(KP * 4);
 #pragma unroll
-                for (int u = 0; u < UNR; ++u)
-                    r[u] = (rem > u * C::SLOTS) ? ((dbg & 2) ? make_uint2(pad_row + (uint32_t)((rem * 37 + u * 11) & 511), 0x3f800000u) : ldg_stream_u2(lp + u * C::SLOTS)) : make_uint2(pad_row, 0u);
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    if (done + u * C::SLOTS >= n) break;  // warp-uniform: no step past the sub-range
-                    const float v = __uint_as_float(r[u].y);
-                    const uint32_t a = tile_q + r[u].x * (uint32_t)(KP * 4);
+                    for (int c4 = 0; c4 < C::NV; ++c4) {
+                        unsigned long long w01, w23, x01, x23;
+                        lds_2x64(a0 + (uint32_t)(c4 * C::LPN * 16), w01, w23);
+                        lds_2x64(a1 + (uint32_t)(c4 * C::LPN * 16), x01, x23);
+                        ffma2(acc[j][2 * c4 + 0], w01, __uint_as_float(rr.y));
+                        ffma2(acc[j][2 * c4 + 1], w23, __uint_as_float(rr.y));
+                        ffma2(acc[j][2 * c4 + 0], x01, __uint_as_float(rr.w));
+                        ffma2(acc[j][2 * c4 + 1], x23, __uint_as_float(rr.w));
+                    }
+                } else {
+                    const uint2 rr = lds_u2(roff);
+                    const uint32_t a0 = tile_q + rr.x * (uint32_t)(KP * 4);
 #pragma unroll
                     for (int c4 = 0; c4 < C::NV; ++c4) {
                         unsigned long long w01, w23;
-                        lds_2x64(a + (uint32_t)(c4 * C::LPN * 16), w01, w23);
-                        ffma2(acc[j][2 * c4 + 0], w01, v);
-                        ffma2(acc[j][2 * c4 + 1], w23, v);
+                        lds_2x64(a0 + (uint32_t)(c4 * C::LPN * 16), w01, w23);
+                        ffma2(acc[j][2 * c4 + 0], w01, __uint_as_float(rr.y));
+                        ffma2(acc[j][2 * c4 + 1], w23, __uint_as_float(rr.y));
                     }
                 }
-                lp += GROUP;
-                rem -= GROUP;
+                pos += C::PAD;
+                if ((pos & (C::CHUNK - 1)) == 0) {  // entering the next chunk: refill the slot just freed
+                    __syncwarp();
+                    fill((int64_t)(pos / C::CHUNK) + C::RC - 1);
+                    cp_async_wait<C::RC - 1>();
+                    __syncwarp();
+                }
             }
         }
-        p0 = p1; p1 = p2; p2 = p3;
+        p0 = p1; p1 = p2;
         __syncthreads();  // every warp is done with stage s
         if (threadIdx.x == 0 && t + 2 < t_end) issue(t + 2);
     }
+    cp_async_wait<0>();
 
     // fold the SLOTS partial sums (lanes with equal q) and store
 #pragma unroll
@@ -229,6 +272,50 @@ __global__ void build_tileptr_kernel(const uint2* __restrict__ rec, const int64_
         }
     }
     tileptr[(int64_t)t * ncol_pad + col] = out;
+}
+
+// padded record count of every (group, tile), flattened as [n_groups][n_tiles + 1] with a zero in the
+// last slot of each row: the exclusive scan of this array is goff.
+__global__ void stream_counts_kernel(const int32_t* __restrict__ tileptr, int64_t ncol, int64_t ncol_pad, int n_tiles,
+                                     int nc, int pad, int64_t n_groups, int64_t* __restrict__ counts) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_groups * (n_tiles + 1)) return;
+    const int64_t grp = e / (n_tiles + 1);
+    const int t = (int)(e % (n_tiles + 1));
+    int64_t tot = 0;
+    if (t < n_tiles) {
+        for (int j = 0; j < nc; ++j) {
+            const int64_t col = grp * nc + j;
+            if (col < ncol) {
+                const int32_t n = tileptr[(int64_t)(t + 1) * ncol_pad + col] - tileptr[(int64_t)t * ncol_pad + col];
+                tot += (n + pad - 1) / pad * pad;
+            }
+        }
+    }
+    counts[e] = tot;
+}
+
+// fill the warp streams from column-compressed records: one warp per (group, tile)
+__global__ void __launch_bounds__(256)
+stream_fill_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ colptr, const int32_t* __restrict__ tileptr,
+                   const int64_t* __restrict__ goff, int64_t ncol, int64_t ncol_pad, int n_tiles, int rb_rows, int nc, int pad,
+                   int64_t n_groups, uint2* __restrict__ stream) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n_groups * n_tiles) return;
+    const int64_t grp = w / n_tiles;
+    const int t = (int)(w % n_tiles);
+    int64_t dst = goff[grp * (n_tiles + 1) + t];
+    const uint2 padrec = make_uint2((uint32_t)(t * rb_rows), 0u);
+    for (int j = 0; j < nc; ++j) {
+        const int64_t col = grp * nc + j;
+        if (col >= ncol) break;
+        const int32_t b = tileptr[(int64_t)t * ncol_pad + col], e = tileptr[(int64_t)(t + 1) * ncol_pad + col];
+        const int32_t n = e - b, np = (n + pad - 1) / pad * pad;
+        const uint2* src = rec + colptr[col] + b;
+        for (int32_t r = lane; r < np; r += 32) stream[dst + r] = (r < n) ? src[r] : padrec;
+        dst += np;
+    }
 }
 
 }  // namespace sgl
