@@ -166,6 +166,16 @@ spmm_stream_kernel(const uint2* __restrict__ stream,     // warp streams (see he
     }
 
     uint32_t pos = 0;  // records consumed so far (multiple of PAD); ring offset = pos % (RC*CHUNK)
+    auto ring_read = [&](uint32_t at) {  // this lane group's record(s) of the fetch step at `at`
+        const uint32_t roff = ring + ((at & (C::RC * C::CHUNK - 1)) + (uint32_t)(C::DS * g)) * 8u;
+        if constexpr (C::DS == 2) {
+            return lds_u4(roff);  // {row0, val0, row1, val1}
+        } else {
+            const uint2 r = lds_u2(roff);
+            return make_uint4(r.x, r.y, 0u, 0u);
+        }
+    };
+    uint4 rr = ring_read(0);
     uint32_t phase0 = 0, phase1 = 0;
     for (int t = t_begin; t < t_end; ++t) {
         const int s = (t - t_begin) & 1;
@@ -182,38 +192,38 @@ spmm_stream_kernel(const uint2* __restrict__ stream,     // warp streams (see he
         for (int j = 0; j < C::NC; ++j) {
             const int32_t steps = __shfl_sync(0xffffffffu, steps_l, j);
             for (int32_t st = 0; st < steps; ++st) {  // warp-uniform
-                const uint32_t roff = ring + ((pos & (C::RC * C::CHUNK - 1)) + (uint32_t)(C::DS * g)) * 8u;
-                if constexpr (C::DS == 2) {
-                    const uint4 rr = lds_u4(roff);  // two records {row0, val0, row1, val1}
-                    const uint32_t a0 = tile_q + rr.x * (uint32_t)(KP * 4);
-                    const uint32_t a1 = tile_q + rr.z * (uint32_t)(KP * 4);
-#pragma unroll
-                    for (int c4 = 0; c4 < C::NV; ++c4) {
-                        unsigned long long w01, w23, x01, x23;
-                        lds_2x64(a0 + (uint32_t)(c4 * C::LPN * 16), w01, w23);
-                        lds_2x64(a1 + (uint32_t)(c4 * C::LPN * 16), x01, x23);
-                        ffma2(acc[j][2 * c4 + 0], w01, __uint_as_float(rr.y));
-                        ffma2(acc[j][2 * c4 + 1], w23, __uint_as_float(rr.y));
-                        ffma2(acc[j][2 * c4 + 0], x01, __uint_as_float(rr.w));
-                        ffma2(acc[j][2 * c4 + 1], x23, __uint_as_float(rr.w));
-                    }
-                } else {
-                    const uint2 rr = lds_u2(roff);
-                    const uint32_t a0 = tile_q + rr.x * (uint32_t)(KP * 4);
-#pragma unroll
-                    for (int c4 = 0; c4 < C::NV; ++c4) {
-                        unsigned long long w01, w23;
-                        lds_2x64(a0 + (uint32_t)(c4 * C::LPN * 16), w01, w23);
-                        ffma2(acc[j][2 * c4 + 0], w01, __uint_as_float(rr.y));
-                        ffma2(acc[j][2 * c4 + 1], w23, __uint_as_float(rr.y));
-                    }
-                }
+                const uint4 cur = rr;
+                // advance, make the chunk under the new position readable, and fetch its records
+                // BEFORE the math of the current ones (software pipelining of the ring read)
                 pos += C::PAD;
                 if ((pos & (C::CHUNK - 1)) == 0) {  // entering the next chunk: refill the slot just freed
                     __syncwarp();
                     fill((int64_t)(pos / C::CHUNK) + C::RC - 1);
                     cp_async_wait<C::RC - 1>();
                     __syncwarp();
+                }
+                rr = ring_read(pos);
+                const uint32_t a0 = tile_q + cur.x * (uint32_t)(KP * 4);
+                if constexpr (C::DS == 2) {
+                    const uint32_t a1 = tile_q + cur.z * (uint32_t)(KP * 4);
+#pragma unroll
+                    for (int c4 = 0; c4 < C::NV; ++c4) {
+                        unsigned long long w01, w23, x01, x23;
+                        lds_2x64(a0 + (uint32_t)(c4 * C::LPN * 16), w01, w23);
+                        lds_2x64(a1 + (uint32_t)(c4 * C::LPN * 16), x01, x23);
+                        ffma2(acc[j][2 * c4 + 0], w01, __uint_as_float(cur.y));
+                        ffma2(acc[j][2 * c4 + 1], w23, __uint_as_float(cur.y));
+                        ffma2(acc[j][2 * c4 + 0], x01, __uint_as_float(cur.w));
+                        ffma2(acc[j][2 * c4 + 1], x23, __uint_as_float(cur.w));
+                    }
+                } else {
+#pragma unroll
+                    for (int c4 = 0; c4 < C::NV; ++c4) {
+                        unsigned long long w01, w23;
+                        lds_2x64(a0 + (uint32_t)(c4 * C::LPN * 16), w01, w23);
+                        ffma2(acc[j][2 * c4 + 0], w01, __uint_as_float(cur.y));
+                        ffma2(acc[j][2 * c4 + 1], w23, __uint_as_float(cur.y));
+                    }
                 }
             }
         }
