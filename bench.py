@@ -40,6 +40,7 @@ CONFIGS = {
     # BASELINE.json configs[2]: the configuration the metric is quoted on
     "c3": dict(m=30000, n=1000000, density=0.05, k=32, name="synthetic 30k genes x 1M cells, 5% density, run_nmf k=32"),
     # smaller stand-ins for quick checks (never the default)
+    "mid": dict(m=30000, n=100000, density=0.05, k=32, name="MID 30k x 100k (not a bench config)"),
     "mini": dict(m=3000, n=20000, density=0.05, k=32, name="MINI 3k x 20k (not a bench config)"),
     "c4shape": dict(m=20000, n=250000, density=0.08, k=16, name="synthetic 20k x 250k, 8% density, k=16 (shape of config 4)"),
 }

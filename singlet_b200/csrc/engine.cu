@@ -97,6 +97,7 @@ struct sgl_handle {
     DevBuf<float> bparts, gram_f, gram_f_nojit, inv_diag;
     DevBuf<double> part, scal, losses, gram_w;
     DevBuf<int64_t> counts;
+    DevBuf<unsigned long long> workctr;
     double* pinned = nullptr;  // 64 doubles of pinned host scratch
     // optional per-kernel-kind event timing (bench.py's roofline numbers are measured live with it)
     bool profiling = false;
@@ -458,20 +459,37 @@ static int dev_update(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask,
     int64_t n_parts = 0;
     if (!mask) {
         if (KPV <= 64) {
-            int nt = 128;
-            DISPATCH_KP(KPV, nt = NnlsCfg<(KP <= 64 ? KP : 64)>::THREADS);
-            n_parts = (X->ncol + nt - 1) / nt;
-            SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
+            // persistent grid: every SM gets as many CTAs as fit, each lane claims columns from a counter
+            static const bool dbg_stats = getenv("SGL_NNLS_STATS") != nullptr;
+            SGL_TRY(h->workctr.ensure(4));
+            if (dbg_stats) {  // print the previous launch's sweep statistics
+                unsigned long long st[4];
+                cudaMemcpyAsync(st, h->workctr.p, sizeof(st), cudaMemcpyDeviceToHost, h->stream);
+                cudaStreamSynchronize(h->stream);
+                if (st[3]) fprintf(stderr, "[nnls] previous launch: %llu columns, mean sweeps %.2f\n", st[3], (double)st[2] / (double)st[3]);
+            }
+            SGL_CUDA(cudaMemsetAsync(h->workctr.p, 0, 4 * sizeof(unsigned long long), h->stream));
             switch (KPV) {
 #define NNLS_CASE(KPC)                                                                                              \
-    case KPC:                                                                                                       \
-        nnls_cols_kernel<KPC><<<(unsigned)n_parts, NnlsCfg<KPC>::THREADS, 0, h->stream>>>(                           \
-            h->bparts.p, splits, F_out, h->gram_f.p, h->inv_diag.p, X->colptr, X->ncol, k, (float)L1, (float)L2, h->part.p); \
-        break;
+    case KPC: {                                                                                                     \
+        static int occ = 0;                                                                                         \
+        if (!occ && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nnls_cols_kernel<KPC>, NnlsCfg<KPC>::THREADS, 0) != cudaSuccess) occ = NnlsCfg<KPC>::MIN_CTAS; \
+        int64_t ctas = (int64_t)h->sm_count * (occ > 0 ? occ : 1);                                                  \
+        const int64_t want = (X->ncol + NnlsCfg<KPC>::THREADS - 1) / NnlsCfg<KPC>::THREADS;                          \
+        if (ctas > want) ctas = want;                                                                               \
+        nnls_cols_kernel<KPC><<<(unsigned)ctas, NnlsCfg<KPC>::THREADS, 0, h->stream>>>(                              \
+            h->bparts.p, splits, F_out, h->gram_f.p, h->inv_diag.p, X->colptr, X->ncol, k, (float)L1, (float)L2, h->workctr.p, dbg_stats ? h->workctr.p + 2 : nullptr); \
+    } break;
                 NNLS_CASE(4) NNLS_CASE(8) NNLS_CASE(16) NNLS_CASE(32) NNLS_CASE(64)
                 default: break;
 #undef NNLS_CASE
             }
+            LAUNCH_CHECK(h);
+            // row sums of the new solution (the local part of scale's d)
+            n_parts = (X->ncol + 255) / 256;
+            if (n_parts > 2 * h->sm_count) n_parts = 2 * h->sm_count;
+            SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
+            DISPATCH_KP(KPV, (rowsum_partial_kernel<KP><<<(unsigned)n_parts, 256, 0, h->stream>>>(F_out, X->ncol, h->part.p)));
         } else {
             n_parts = (X->ncol + 31) / 32;
             SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
@@ -831,7 +849,7 @@ int sgl_destroy(sgl_handle* h) {
     matrix_release(h->cA);
     matrix_release(h->cAt);
     h->bparts.release(); h->gram_f.release(); h->gram_f_nojit.release(); h->inv_diag.release();
-    h->part.release(); h->scal.release(); h->losses.release(); h->gram_w.release(); h->counts.release();
+    h->part.release(); h->scal.release(); h->losses.release(); h->gram_w.release(); h->counts.release(); h->workctr.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);

@@ -75,6 +75,11 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
     return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
 
+// Persistent variant with lane refill: columns converge after very different numbers of sweeps
+// (from ~30 to the 100-sweep cap once the factors have separated; early iterations hit the cap), so a lane whose column is done immediately
+// writes it back and claims the next unsolved column from a global counter instead of idling until
+// the slowest lane of its warp finishes. Columns are independent, so the result does not depend on
+// which lane solves which column. Row sums are taken afterwards by rowsum_partial_kernel.
 template <int KP>
 __global__ void __launch_bounds__(NnlsCfg<KP>::THREADS, NnlsCfg<KP>::MIN_CTAS)
 nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
@@ -82,70 +87,94 @@ nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
                  const float* __restrict__ gram_f,   // [KP][KP] float (symmetric)
                  const float* __restrict__ inv_diag, // [KP]
                  const int64_t* __restrict__ colptr, int64_t ncol, int k, float L1, float L2,
-                 double* __restrict__ rowsum_part)   // [gridDim.x][KP]
+                 unsigned long long* __restrict__ next_col,  // global work counter (zeroed by the host)
+                 unsigned long long* __restrict__ stats)     // optional: [0] += sweeps, [1] += columns solved
 {
     constexpr int NT = NnlsCfg<KP>::THREADS;
-    constexpr int KP2 = (KP + 1) / 2 * 2;
     __shared__ __align__(16) float sa[KP * KP];
     __shared__ float sinv[KP];
     __shared__ float sx[KP * NT];  // sx[i * NT + tid]
-    __shared__ double sred[NT / 32][KP];
 
     for (int t = threadIdx.x; t < KP * KP; t += NT) sa[t] = gram_f[t];
     for (int t = threadIdx.x; t < KP; t += NT) sinv[t] = inv_diag[t];
     __syncthreads();
 
-    const int64_t col = (int64_t)blockIdx.x * NT + threadIdx.x;
-    const bool in_range = col < ncol;
-    const bool solve = in_range && (colptr[col] != colptr[col + 1]);  // empty columns are skipped (:340)
-
-    // b as packed FP32 pairs so that the rank-1 update runs on FFMA2
-    unsigned long long b2[KP2 / 2];
-    {
-        float b[KP];
+    const int lane = threadIdx.x & 31;
+    unsigned long long b2[KP / 2];  // b as packed FP32 pairs (the rank-1 update runs on FFMA2)
 #pragma unroll
-        for (int j = 0; j < KP; ++j) b[j] = 0.f;
-        if (in_range) {
-            for (int s = 0; s < splits; ++s) {
-                const float4* src = reinterpret_cast<const float4*>(Bparts + ((int64_t)s * ncol + col) * KP);
-#pragma unroll
-                for (int j4 = 0; j4 < KP / 4; ++j4) {
-                    const float4 v = src[j4];
-                    b[4 * j4 + 0] += v.x; b[4 * j4 + 1] += v.y; b[4 * j4 + 2] += v.z; b[4 * j4 + 3] += v.w;
-                }
-            }
-            const float4* xs = reinterpret_cast<const float4*>(X + col * KP);
-#pragma unroll
-            for (int j4 = 0; j4 < KP / 4; ++j4) {
-                const float4 v = xs[j4];
-                sx[(4 * j4 + 0) * NT + threadIdx.x] = v.x; sx[(4 * j4 + 1) * NT + threadIdx.x] = v.y;
-                sx[(4 * j4 + 2) * NT + threadIdx.x] = v.z; sx[(4 * j4 + 3) * NT + threadIdx.x] = v.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < KP; ++j) sx[j * NT + threadIdx.x] = 0.f;
-        }
-#pragma unroll
-        for (int j2 = 0; j2 < KP / 2; ++j2) b2[j2] = pack2(b[2 * j2], b[2 * j2 + 1]);
-    }
-
-    bool active = solve;
+    for (int j2 = 0; j2 < KP / 2; ++j2) b2[j2] = 0ull;
+    int64_t col = -1;     // column being solved by this lane (-1: none)
+    bool exhausted = false;  // the counter ran past ncol
     float tol = 1.f;
+    int sweeps = 0;
     const float kf = (float)k;
     const uint32_t sa_addr = smem_u32(sa);
-    for (int sweep = 0; sweep < NNLS_MAX_SWEEPS; ++sweep) {
-        active = active && (tol / kf > 1e-8f);
+
+    while (true) {
+        // ---- retire finished columns and claim new ones (per lane; the warp takes this path together) ----
+        const bool finished = (col >= 0) && (sweeps >= NNLS_MAX_SWEEPS || !(tol / kf > 1e-8f));
+        bool need = (col < 0 || finished) && !exhausted;
+        if (finished) {
+            if (stats) { atomicAdd(&stats[0], (unsigned long long)sweeps); atomicAdd(&stats[1], 1ull); }
+            float4* xd = reinterpret_cast<float4*>(X + col * KP);
+#pragma unroll
+            for (int j4 = 0; j4 < KP / 4; ++j4)
+                xd[j4] = make_float4(sx[(4 * j4 + 0) * NT + threadIdx.x], sx[(4 * j4 + 1) * NT + threadIdx.x],
+                                     sx[(4 * j4 + 2) * NT + threadIdx.x], sx[(4 * j4 + 3) * NT + threadIdx.x]);
+            col = -1;
+        }
+        while (__any_sync(0xffffffffu, need)) {
+            const uint32_t mask = __ballot_sync(0xffffffffu, need);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(next_col, (unsigned long long)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (need) {
+                const int64_t c = (int64_t)base + __popc(mask & ((1u << lane) - 1u));
+                if (c >= ncol) {
+                    exhausted = true;
+                    need = false;
+                } else if (colptr[c] != colptr[c + 1]) {  // empty columns are skipped (:340)
+                    float b[KP];
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) b[j] = 0.f;
+                    for (int s = 0; s < splits; ++s) {
+                        const float4* src = reinterpret_cast<const float4*>(Bparts + ((int64_t)s * ncol + c) * KP);
+#pragma unroll
+                        for (int j4 = 0; j4 < KP / 4; ++j4) {
+                            const float4 v = src[j4];
+                            b[4 * j4 + 0] += v.x; b[4 * j4 + 1] += v.y; b[4 * j4 + 2] += v.z; b[4 * j4 + 3] += v.w;
+                        }
+                    }
+#pragma unroll
+                    for (int j2 = 0; j2 < KP / 2; ++j2) b2[j2] = pack2(b[2 * j2], b[2 * j2 + 1]);
+                    const float4* xs = reinterpret_cast<const float4*>(X + c * KP);
+#pragma unroll
+                    for (int j4 = 0; j4 < KP / 4; ++j4) {
+                        const float4 v = xs[j4];
+                        sx[(4 * j4 + 0) * NT + threadIdx.x] = v.x; sx[(4 * j4 + 1) * NT + threadIdx.x] = v.y;
+                        sx[(4 * j4 + 2) * NT + threadIdx.x] = v.z; sx[(4 * j4 + 3) * NT + threadIdx.x] = v.w;
+                    }
+                    col = c;
+                    tol = 1.f;
+                    sweeps = 0;
+                    need = false;
+                }  // else: empty column, claim another one
+            }
+        }
+        const bool active = col >= 0;
         if (!__any_sync(0xffffffffu, active)) break;
+
+        // ---- one sweep (src/singlet.cpp:231-248) for every lane that holds a column ----
         tol = 0.f;
+        ++sweeps;
 #pragma unroll
         for (int i = 0; i < KP; ++i) {
             if (i < k) {  // uniform
-                const float xi_old = sx[i * NT + threadIdx.x];
-                float xi = xi_old, tl = tol;
+                float xi = sx[i * NT + threadIdx.x], tl = tol;
                 const float bi = (i & 1) ? hi32(b2[i >> 1]) : lo32(b2[i >> 1]);
                 float mult = cd_step_nb(bi, sinv[i], xi, L1, L2, tl);
                 mult = active ? mult : 0.f;
-                tol = active ? tl : tol;
+                tol = tl;
                 if (active) sx[i * NT + threadIdx.x] = xi;
 #pragma unroll
                 for (int j4 = 0; j4 < KP / 4; ++j4) {
@@ -157,28 +186,24 @@ nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
             }
         }
     }
+}
 
-    // write back + row sums of the solution (all columns of the block, skipped ones included:
-    // `scale` sums every column, src/singlet.cpp:220)
-    float xo[KP];
-#pragma unroll
-    for (int j = 0; j < KP; ++j) xo[j] = sx[j * NT + threadIdx.x];
-    if (solve) {
-        float4* xd = reinterpret_cast<float4*>(X + col * KP);
-#pragma unroll
-        for (int j4 = 0; j4 < KP / 4; ++j4) xd[j4] = make_float4(xo[4 * j4], xo[4 * j4 + 1], xo[4 * j4 + 2], xo[4 * j4 + 3]);
-    }
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-        const double s = warp_sum((double)xo[j]);
-        if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5][j] = s;
-    }
+// row sums of X [cols][KP] in FP64: per-CTA partials [grid][KP], reduced in fixed order afterwards
+template <int KP>
+__global__ void __launch_bounds__(256)
+rowsum_partial_kernel(const float* __restrict__ X, int64_t cols, double* __restrict__ part) {
+    constexpr int CPI = 256 / KP;  // columns per pass (KP <= 128 -> >= 2)
+    __shared__ double sm[256];
+    const int f = threadIdx.x % KP, sub = threadIdx.x / KP;
+    double s = 0.0;
+    for (int64_t c = (int64_t)blockIdx.x * CPI + sub; c < cols; c += (int64_t)gridDim.x * CPI) s += (double)X[c * KP + f];
+    sm[threadIdx.x] = s;
     __syncthreads();
-    for (int t = threadIdx.x; t < KP; t += NT) {
-        double s = 0.0;
+    if (threadIdx.x < KP) {
+        double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < NT / 32; ++w) s += sred[w][t];  // fixed order: deterministic
-        rowsum_part[(int64_t)blockIdx.x * KP + t] = s;
+        for (int q = 0; q < CPI; ++q) t += sm[q * KP + threadIdx.x];
+        part[(int64_t)blockIdx.x * KP + threadIdx.x] = t;
     }
 }
 
