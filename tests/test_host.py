@@ -1,0 +1,119 @@
+"""Host-side logic that needs no GPU: R RNG restatement, fixture reader, synthetic generator rules,
+the C-ABI library's symbol table, the rank-selection controller."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_r_rng_matches_r():
+    """set.seed(123); runif(5) and .Random.seed[3] are R's well-known values."""
+    from singlet_b200.rrng import RRng
+
+    r = RRng(123)
+    assert r.dot_random_seed(1) == 10403 and r.dot_random_seed(2) == 624
+    assert r.dot_random_seed(3) == -983674937
+    assert np.allclose(r.runif(5), [0.28757752, 0.78830514, 0.40897692, 0.88301740, 0.94046728], atol=5e-9)
+    m = RRng(42).matrix_runif(3, 4)
+    assert m.shape == (3, 4) and np.allclose(m.ravel(order="F"), RRng(42).runif(12))  # column-major fill
+    a = RRng(7)
+    a.runif(700)  # crosses one 624-word regeneration
+    assert a.dot_random_seed(2) == 700 - 624
+
+
+def test_pbmc3k_fixture():
+    """Shape and summary statistics of the bundled dataset."""
+    from singlet_b200.datasets import get_pbmc3k_data, log_normalize
+
+    A = get_pbmc3k_data()
+    assert A.shape == (13714, 2700) and A.nnz == 2282976
+    assert A.data.max() == 419 and abs(A.data.mean() - 2.797) < 1e-3
+    assert A.has_sorted_indices and np.diff(A.indptr).min() == 212 and np.diff(A.indptr).max() == 3400
+    N = log_normalize(A)
+    assert abs(N.data.mean() - 2.026) < 1e-3
+    src = "/root/reference/data/pbmc3k.RData"
+    if os.path.exists(src):
+        B = get_pbmc3k_data(src)
+        assert (A != B).nnz == 0
+
+
+def test_synth_rules():
+    from singlet_b200 import synth
+
+    S, q32, table = synth.spec(30000, 0.05)
+    assert S == 10 and q32 == round(0.5 * 2**32) and table.dtype == np.float32 and np.all(np.diff(table) > 0)
+    A = synth.synth_scipy(2000, 1500, 0.05)
+    assert abs(A.nnz / (2000 * 1500) - 0.05) < 0.002 and A.has_sorted_indices
+    B = synth.synth_csc(2000, 1500, 0.05, col0=100, ncol=50)
+    S_ = A[:, 100:150]
+    assert np.array_equal(B[0], S_.indptr) and np.array_equal(B[1], S_.indices) and np.array_equal(B[2], S_.data)
+    w = synth.w_init(4, 10)
+    assert w.shape == (4, 10) and w.min() > 0 and w.max() < 1 and w.flags.f_contiguous
+    assert synth.algorithmic_bytes_per_iter(30000, 10**6, 1_500_000_000, 32) == 16 * 1_500_000_000 + 4 * 1030002 + 16 * 32 * 1030000
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """libsinglet_cuda.so loads without a GPU and exports exactly what include/singlet_cuda.h declares."""
+    from singlet_b200 import _lib
+
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "singlet_cuda.h")).read()
+    declared = set(re.findall(r"\b(sgl_[a-z0-9_]+)\s*\(", hdr))
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    assert declared == bound, (declared ^ bound)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.sgl_version() >= 100
+    assert [lib.sgl_padded_rank(k) for k in (1, 4, 5, 10, 32, 33, 100, 128, 129)] == [4, 4, 8, 16, 32, 64, 128, 128, -1]
+    s = np.array([3.0, 6.0, 8.0, 5.0, 14.0])  # x = (0,1,2), y = (1,2,3): sum x, sum y, sum xy, sum x^2, sum y^2
+    assert abs(lib.sgl_cor_from_sums(s.ctypes.data, 3.0)) < 1e-12
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product path fails loudly instead of falling back."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from singlet_b200 import SingletCudaError, api, synth
+
+    A = synth.synth_scipy(50, 40, 0.2)
+    with pytest.raises(SingletCudaError) as e:
+        api.c_nmf(A, A.T.tocsc(), 1e-4, 2, False, 0, 0, 0, 0, 0, synth.w_init(2, 50), handle=api.Handle(0))
+    assert e.value.code == -2
+
+
+def test_get_best_rank():
+    """R/GetBestRank.R:8-46 on hand-made CV tables."""
+    import pandas as pd
+
+    from singlet_b200.api import GetBestRank
+
+    rows = []
+    for rep in (1, 2):
+        for k, errs in ((2, [0.20, 0.15, 0.14]), (4, [0.18, 0.13, 0.12]), (8, [0.17, 0.12, 0.125])):
+            for it, e in enumerate(errs):
+                rows.append({"k": k, "rep": rep, "test_error": e, "iter": 5 * it, "tol": 1e-3})
+    df = pd.DataFrame(rows)
+    assert GetBestRank(df, 1e-4) == 4  # k = 8 overfits (error rises), so it and above are excluded
+    assert GetBestRank(df[df["k"] < 8], 1e-4) == 4
+    assert GetBestRank(df, 0.5) == 4  # loose threshold: nothing counts as overfit, lowest final error (k = 4) wins
+    df2 = df.copy()
+    df2.loc[(df2["k"] == 8) & (df2["iter"] == 10), "test_error"] = 0.11  # k = 8 keeps improving
+    assert GetBestRank(df2, 1e-4) == 8
+
+
+def test_distributed_transpose_blocks():
+    """R/cross_validate_nmf.R:37-50: gene-block transposes of a column-chunk list."""
+    from singlet_b200 import api, synth
+
+    A = synth.synth_scipy(103, 60, 0.2)
+    chunks = [A[:, :20].tocsc(), A[:, 20:45].tocsc(), A[:, 45:].tocsc()]
+    blocks = api._distributed_transpose(chunks)
+    assert len(blocks) == 3 and all(b.shape[0] == 60 for b in blocks) and sum(b.shape[1] for b in blocks) == 103
+    import scipy.sparse as sp
+
+    assert (sp.hstack(blocks).tocsc() != A.T.tocsc()).nnz == 0

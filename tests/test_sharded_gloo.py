@@ -1,0 +1,177 @@
+"""The N > 1 path on CPU: two gloo ranks run singlet_b200.sharded.ShardedNMF with a TEST-ONLY backend
+whose compute calls go to the CPU oracle. This checks the sharding logic -- shard bounds, global
+hash offsets, which quantities are all-reduced / all-gathered and when -- against the unsharded
+oracle fit. (The product backend is CudaBackend; nothing in singlet_b200/ can reach this one.)"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBackend:
+    """Same interface as singlet_b200.sharded.CudaBackend, FP64 on CPU tensors, solves via the oracle."""
+
+    def __init__(self):
+        from oracle.pyoracle import Oracle
+
+        self.orc = Oracle("port")
+
+    def kp(self, k):
+        kp = 4
+        while kp < k:
+            kp <<= 1
+        return kp
+
+    def zeros_factor(self, cols, k):
+        return torch.zeros((max(cols, 1), self.kp(k)), dtype=torch.float64)
+
+    def zeros_f64(self, n):
+        return torch.zeros(n, dtype=torch.float64)
+
+    def factor_from_host(self, host_kxc, out):
+        k, cols = host_kxc.shape
+        out[:cols, :k] = torch.from_numpy(np.ascontiguousarray(host_kxc.T))
+
+    def factor_to_host(self, dev, k, cols):
+        return np.asfortranarray(dev[:cols, :k].numpy().T)
+
+    def upload(self, A):
+        return A.tocsc()
+
+    def mask_build(self, X, seed, inv_density, mask_t, col_offset, row_offset):
+        return (seed, inv_density, mask_t, col_offset, row_offset)
+
+    def gram(self, F, k, cols, out, jitter):
+        kp = self.kp(k)
+        g = np.zeros((kp, kp))
+        f = F[:cols, :k].numpy()
+        g[:k, :k] = f.T @ f
+        if jitter:
+            g[np.arange(k), np.arange(k)] += 1e-15
+        out.copy_(torch.from_numpy(g.ravel()))
+
+    def gram_jitter(self, k, gram):
+        kp = self.kp(k)
+        g = gram.view(kp, kp)
+        for f in range(k):
+            g[f, f] += 1e-15
+
+    def update(self, X, mask, F_in, F_out, k, gram, L1, L2, rowsum):
+        kp = self.kp(k)
+        a = gram.view(kp, kp)[:k, :k].numpy().copy()
+        Fi = F_in[:, :k].numpy()
+        for c in range(X.shape[1]):
+            lo, hi = X.indptr[c], X.indptr[c + 1]
+            if lo == hi:
+                continue
+            rows, vals = X.indices[lo:hi], X.data[lo:hi]
+            ai = a
+            if mask is not None:
+                seed, inv, mask_t, coff, roff = mask
+                gc = c + coff
+                held = np.array([self.orc.draw(seed, r + roff, gc, inv) if mask_t else self.orc.draw(seed, gc, r + roff, inv)
+                                 for r in range(X.shape[0])], dtype=bool)
+                keep = ~held[rows]
+                rows, vals = rows[keep], vals[keep]
+                fm = Fi[np.nonzero(held)[0]]
+                ai = a - (fm.T @ fm + 1e-15 * np.eye(k))
+            b = Fi[rows].T @ vals if len(rows) else np.zeros(k)
+            x, _, _ = self.orc.nnls(ai, b, F_out[c, :k].numpy(), L1, L2)
+            F_out[c, :k] = torch.from_numpy(x)
+        rs = torch.zeros(kp, dtype=torch.float64)
+        rs[:k] = F_out[: X.shape[1], :k].sum(dim=0)
+        rowsum.copy_(rs)
+
+    def finish_d(self, k, d):
+        d[:k] += 1e-15
+        d[k:] = 1.0
+
+    def scale(self, F, k, cols, d):
+        F[:cols, :k] /= d[:k]
+
+    def cor_sums(self, X, Y, k, cols, out):
+        x, y = X[:cols, :k].numpy().ravel(), Y[:cols, :k].numpy().ravel()
+        out[:5] = torch.tensor([x.sum(), y.sum(), (x * y).sum(), (x * x).sum(), (y * y).sum()], dtype=torch.float64)
+
+    def cor_from_sums(self, s, n):
+        return float(1 - (n * s[2] - s[0] * s[1]) / np.sqrt((n * s[3] - s[0] ** 2) * (n * s[4] - s[1] ** 2)))
+
+    def mse(self, A, mask, W, d, H, k, which, out):
+        seed, inv, mask_t, coff, roff = mask
+        wd = W[: A.shape[0], :k].numpy() * d[:k].numpy()
+        tot = 0.0
+        for c in range(A.shape[1]):
+            held = np.array([self.orc.draw(seed, c + coff, g, inv) for g in range(A.shape[0])], dtype=bool)
+            if held.any():
+                col = np.asarray(A[:, c].todense()).ravel()
+                res = wd[held] @ H[c, :k].numpy() - col[held]
+                tot += float((res ** 2).mean())
+        out[0] = tot
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from singlet_b200 import synth
+        from singlet_b200.sharded import shard_bounds, sharded_ard_nmf, sharded_nmf
+
+        m, n, k = 41, 37, 3  # ragged on purpose: neither divides by 2
+        A = synth.synth_scipy(m, n, 0.3, seed=5)
+        At = A.T.tocsc()
+        w0 = synth.w_init(k, m, seed=2)
+        c0, c1, _ = shard_bounds(n, world, rank)
+        g0, g1, _ = shard_bounds(m, world, rank)
+        be = OracleBackend()
+        res = sharded_nmf(be, m, n, k, A[:, c0:c1].tocsc(), At[:, g0:g1].tocsc(), w0, tol=0.0, maxit=4, L1=(0.01, 0.02),
+                          rank=rank, world=world)
+        cv = sharded_ard_nmf(be, m, n, k, A[:, c0:c1].tocsc(), At[:, g0:g1].tocsc(), w0, 123, 5, tol=0.0, maxit=3,
+                             overfit_threshold=10.0, trace_test_mse=2, rank=rank, world=world)
+        q.put((rank, res["w"], res["h"], res["d"], res["tol"], cv["test_mse"], cv["h"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_matches_unsharded_oracle(oracle):
+    from singlet_b200 import synth
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m, n, k = 41, 37, 3
+    A = synth.synth_scipy(m, n, 0.3, seed=5)
+    At = A.T.tocsc()
+    w0 = synth.w_init(k, m, seed=2)
+    ref = oracle.nmf(A, At, w0, tol=0.0, maxit=4, L1=(0.01, 0.02))
+    cvr = oracle.ard_nmf(A, At, w0, 123, 5, tol=0.0, maxit=3, overfit_threshold=10.0, trace_test_mse=2)
+    for rank, w, h, d, tol, mse, hcv in outs:  # every rank ends with the full replicated model
+        assert np.allclose(w, ref["w"], rtol=1e-9, atol=1e-12) and np.allclose(h, ref["h"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(d, ref["d"], rtol=1e-9) and abs(tol - ref["tol"][-1]) < 1e-9
+        assert np.allclose(mse, cvr["test_mse"], rtol=1e-9) and np.allclose(hcv, cvr["h"], rtol=1e-8, atol=1e-12)
+
+
+def test_shard_bounds_cover_everything():
+    from singlet_b200.sharded import shard_bounds
+
+    for total in (1, 7, 8, 30000, 1000003):
+        for world in (1, 2, 3, 8):
+            seen = 0
+            for r in range(world):
+                lo, hi, per = shard_bounds(total, world, r)
+                assert lo == min(r * per, total) and lo <= hi <= total
+                seen += hi - lo
+            assert seen == total
