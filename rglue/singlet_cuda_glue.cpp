@@ -1,0 +1,163 @@
+// singlet_cuda_glue.cpp -- drop-in bodies for the reference's Rcpp entry points on the ALS-NMF path.
+//
+// This file REPLACES the bodies of c_nmf, c_nmf_sparse_list, c_ard_nmf, c_ard_nmf_sparse_list,
+// c_project_model and Rcpp_predict in the reference's src/singlet.cpp (lines 350-367, 405-413, 669-672,
+// 715-743, 1155-1234). Their signatures are unchanged, so the auto-generated shims in
+// src/RcppExports.cpp (:67-116, :138-155, :283-327) and the R wrappers in R/RcppExports.R keep working
+// byte for byte. Everything below only unpacks the R objects, calls the C ABI of libsinglet_cuda.so
+// (include/singlet_cuda.h) and wraps the results. R is not installed in the build container, so this
+// file is compiled where the package is built; the same calls are exercised
+// from Python (singlet_b200/api.py) in the test-suite.
+#include <Rcpp.h>
+#include <RcppEigen.h>
+#include <singlet.h>  // Rcpp::SparseMatrix (inst/include/singlet.h:36-102)
+
+#include <vector>
+
+#include "singlet_cuda.h"
+
+namespace {
+
+sgl_handle* handle() {  // one handle per R session: keeps A/At and the CV mask resident between calls
+    static sgl_handle* h = nullptr;
+    if (!h && sgl_create(0, nullptr, &h) != SGL_OK) Rcpp::stop(sgl_last_error());
+    return h;
+}
+
+sgl_csc view(Rcpp::SparseMatrix& A) {  // zero-copy: points at the dgCMatrix slots
+    sgl_csc c;
+    c.nrow = A.rows();
+    c.ncol = A.cols();
+    c.p = A.p.begin();
+    c.i = A.i.begin();
+    c.x = A.x.begin();
+    return c;
+}
+std::vector<sgl_csc> views(std::vector<Rcpp::SparseMatrix>& v) {
+    std::vector<sgl_csc> out;
+    for (auto& m : v) out.push_back(view(m));
+    return out;
+}
+std::vector<Rcpp::SparseMatrix> as_list(Rcpp::List& L) {
+    std::vector<Rcpp::SparseMatrix> v;
+    for (auto&& e : L) v.push_back(Rcpp::as<Rcpp::SparseMatrix>(e));
+    return v;
+}
+
+// Rprintf / checkUserInterrupt of src/singlet.cpp:643-663, 1102-1128, driven from the library's callbacks
+struct Progress {
+    bool verbose, masked;
+};
+void on_iter(void* u, int iter, double tol, double overfit) {
+    Progress* p = static_cast<Progress*>(u);
+    if (!p->verbose) return;
+    if (!p->masked) Rprintf("%4d | %8.2e\n", iter, tol);
+    else if (ISNAN(overfit)) Rprintf("%4d | %8.2e | %8s\n", iter, tol, "-");
+    else Rprintf("%4d | %8.2e | %8.2e\n", iter, tol, overfit);
+}
+void check_interrupt_fn(void*) { R_CheckUserInterrupt(); }
+int poll_interrupt(void*) {  // R_ToplevelExec returns FALSE when the user interrupted
+    return R_ToplevelExec(check_interrupt_fn, nullptr) == FALSE ? 1 : 0;
+}
+sgl_callbacks callbacks(Progress& p) {
+    sgl_callbacks cb;
+    cb.user = &p;
+    cb.poll_interrupt = poll_interrupt;
+    cb.on_iter = on_iter;
+    return cb;
+}
+void check(int rc) {
+    if (rc == SGL_EINTERRUPT) Rcpp::stop("interrupted");  // the library has already unwound and freed
+    if (rc != SGL_OK) Rcpp::stop(sgl_last_error());
+}
+
+Rcpp::List nmf_impl(std::vector<sgl_csc> A, std::vector<sgl_csc> At, double tol, uint16_t maxit, bool verbose, double L1_w,
+                    double L1_h, double L2_w, double L2_h, Eigen::MatrixXd& w) {
+    const int k = (int)w.rows();
+    int64_t n = 0;
+    for (auto& c : A) n += c.ncol;
+    Eigen::MatrixXd h(k, n);
+    Eigen::VectorXd d(k);
+    Progress p{verbose, false};
+    sgl_callbacks cb = callbacks(p);
+    if (verbose) Rprintf("\n%4s | %8s \n---------------\n", "iter", "tol");
+    check(sgl_nmf(handle(), A.data(), (int)A.size(), At.data(), (int)At.size(), tol, maxit, L1_w, L1_h, L2_w, L2_h, k, w.data(),
+                  d.data(), h.data(), nullptr, nullptr, &cb));
+    return Rcpp::List::create(Rcpp::Named("w") = w, Rcpp::Named("d") = d, Rcpp::Named("h") = h);
+}
+
+Rcpp::List ard_impl(std::vector<sgl_csc> A, std::vector<sgl_csc> At, double tol, uint16_t maxit, bool verbose, double L1, double L2,
+                    Eigen::MatrixXd& w, uint64_t seed, uint64_t inv_density, double overfit_threshold, uint16_t trace_test_mse) {
+    const int k = (int)w.rows();
+    int64_t n = 0;
+    for (auto& c : A) n += c.ncol;
+    Eigen::MatrixXd h(k, n);
+    Eigen::VectorXd d(k);
+    const int cap = (int)maxit + 2;
+    std::vector<double> mse(cap), ft(cap), so(cap);
+    std::vector<int32_t> it(cap);
+    sgl_trace tr{mse.data(), it.data(), ft.data(), so.data(), cap, 0};
+    Progress p{verbose, true};
+    sgl_callbacks cb = callbacks(p);
+    if (verbose) Rprintf("\n%4s | %8s | %8s \n---------------------------\n", "iter", "tol", "overfit");
+    check(sgl_ard_nmf(handle(), A.data(), (int)A.size(), At.data(), (int)At.size(), tol, maxit, L1, L2, k, w.data(), d.data(),
+                      h.data(), seed, inv_density, overfit_threshold, trace_test_mse, &tr, &cb));
+    Rcpp::NumericVector test_mse(mse.begin(), mse.begin() + tr.length), fit_tol(ft.begin(), ft.begin() + tr.length),
+        score(so.begin(), so.begin() + tr.length);
+    Rcpp::IntegerVector iter(it.begin(), it.begin() + tr.length);
+    return Rcpp::List::create(Rcpp::Named("w") = w, Rcpp::Named("d") = d, Rcpp::Named("h") = h, Rcpp::Named("test_mse") = test_mse,
+                              Rcpp::Named("iter") = iter, Rcpp::Named("tol") = fit_tol, Rcpp::Named("score_overfit") = score);
+}
+
+}  // namespace
+
+//[[Rcpp::export]]
+Rcpp::List c_nmf(Rcpp::SparseMatrix& A, Rcpp::SparseMatrix& At, const double tol, const uint16_t maxit, const bool verbose,
+                 const double L1_w, const double L1_h, const double L2_w, const double L2_h, const uint16_t threads,
+                 Eigen::MatrixXd w) {
+    return nmf_impl({view(A)}, {view(At)}, tol, maxit, verbose, L1_w, L1_h, L2_w, L2_h, w);
+}
+
+//[[Rcpp::export]]
+Rcpp::List c_nmf_sparse_list(Rcpp::List A_, Rcpp::List& At_, const double tol, const uint16_t maxit, const bool verbose,
+                             const double L1, const double L2, const uint16_t threads, Eigen::MatrixXd w) {
+    std::vector<Rcpp::SparseMatrix> A = as_list(A_), At = as_list(At_);
+    return nmf_impl(views(A), views(At), tol, maxit, verbose, L1, L1, L2, L2, w);
+}
+
+//[[Rcpp::export]]
+Rcpp::List c_ard_nmf(Rcpp::SparseMatrix& A, Rcpp::SparseMatrix& At, const double tol, const uint16_t maxit, const bool verbose,
+                     const double L1, const double L2, const uint16_t threads, Eigen::MatrixXd w, const uint64_t seed,
+                     const uint64_t inv_density, const double overfit_threshold, const uint16_t trace_test_mse) {
+    return ard_impl({view(A)}, {view(At)}, tol, maxit, verbose, L1, L2, w, seed, inv_density, overfit_threshold, trace_test_mse);
+}
+
+//[[Rcpp::export]]
+Rcpp::List c_ard_nmf_sparse_list(Rcpp::List A_, Rcpp::List At_, const double tol, const uint16_t maxit, const bool verbose,
+                                 const double L1, const double L2, const uint16_t threads, Eigen::MatrixXd w,
+                                 const uint64_t rng_seed, const uint64_t inv_density, const double overfit_threshold,
+                                 const uint16_t trace_test_mse) {
+    std::vector<Rcpp::SparseMatrix> A = as_list(A_), At = as_list(At_);
+    return ard_impl(views(A), views(At), tol, maxit, verbose, L1, L2, w, rng_seed, inv_density, overfit_threshold, trace_test_mse);
+}
+
+//[[Rcpp::export]]
+Rcpp::List c_project_model(Rcpp::SparseMatrix A, Eigen::MatrixXd w, const double L1, const double L2, const int threads) {
+    const int64_t m = A.rows();
+    const int k = (int)((w.rows() == m) ? w.cols() : w.rows());
+    Eigen::MatrixXd h(k, (int64_t)A.cols());
+    Eigen::VectorXd d(k);
+    sgl_csc a = view(A);
+    check(sgl_project_model(handle(), &a, 1, w.data(), w.rows(), w.cols(), L1, L2, h.data(), d.data()));
+    return Rcpp::List::create(Rcpp::Named("h") = h, Rcpp::Named("d") = d);
+}
+
+//[[Rcpp::export]]
+Eigen::MatrixXd Rcpp_predict(Rcpp::SparseMatrix A, Eigen::MatrixXd w, const double L1, const double L2, const int threads) {
+    const int64_t m = A.rows();
+    const int k = (int)((w.rows() == m && w.cols() != m) ? w.cols() : w.rows());
+    Eigen::MatrixXd h(k, (int64_t)A.cols());
+    sgl_csc a = view(A);
+    check(sgl_predict(handle(), &a, 1, w.data(), w.rows(), w.cols(), L1, L2, h.data()));
+    return h;
+}

@@ -469,6 +469,9 @@ static int dev_update(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask,
                 if (st[3]) fprintf(stderr, "[nnls] previous launch: %llu columns, mean sweeps %.2f\n", st[3], (double)st[2] / (double)st[3]);
             }
             SGL_CUDA(cudaMemsetAsync(h->workctr.p, 0, 4 * sizeof(unsigned long long), h->stream));
+            // Gram + reciprocal diagonal -> constant memory (uniform-datapath operands of the solver)
+            SGL_CUDA(cudaMemcpyToSymbolAsync(c_gram, h->gram_f.p, sizeof(float) * KPV * KPV, 0, cudaMemcpyDeviceToDevice, h->stream));
+            SGL_CUDA(cudaMemcpyToSymbolAsync(c_inv_diag, h->inv_diag.p, sizeof(float) * KPV, 0, cudaMemcpyDeviceToDevice, h->stream));
             switch (KPV) {
 #define NNLS_CASE(KPC)                                                                                              \
     case KPC: {                                                                                                     \
@@ -478,7 +481,7 @@ static int dev_update(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask,
         const int64_t want = (X->ncol + NnlsCfg<KPC>::THREADS - 1) / NnlsCfg<KPC>::THREADS;                          \
         if (ctas > want) ctas = want;                                                                               \
         nnls_cols_kernel<KPC><<<(unsigned)ctas, NnlsCfg<KPC>::THREADS, 0, h->stream>>>(                              \
-            h->bparts.p, splits, F_out, h->gram_f.p, h->inv_diag.p, X->colptr, X->ncol, k, (float)L1, (float)L2, h->workctr.p, dbg_stats ? h->workctr.p + 2 : nullptr); \
+            h->bparts.p, splits, F_out, X->colptr, X->ncol, k, (float)L1, (float)L2, h->workctr.p, dbg_stats ? h->workctr.p + 2 : nullptr); \
     } break;
                 NNLS_CASE(4) NNLS_CASE(8) NNLS_CASE(16) NNLS_CASE(32) NNLS_CASE(64)
                 default: break;

@@ -48,19 +48,22 @@ __device__ __forceinline__ float cd_step(float bi, float inv_aii, float& xi, flo
 template <int KP>
 struct NnlsCfg {
     static constexpr int THREADS = (KP <= 32) ? 128 : 64;
-    static constexpr int MIN_CTAS = (KP <= 32) ? 3 : 2;  // register cap: 128 (KP<=32) / 170 (KP=64)
+    static constexpr int MIN_CTAS = (KP <= 32) ? 3 : 2;  // register cap: 170 (KP<=32) / 255 (KP=64)
 };
 
 // branch-free coordinate step (same arithmetic as cd_step): returns MINUS the delta, i.e. the
 // multiplier m of  b += a[:, i] * m.
 __device__ __forceinline__ float cd_step_nb(float bi, float inv_aii, float& xi, float L1, float L2, float& tol) {
-    const float diff = fmaf(L2, xi, bi * inv_aii - L1);
+    const float diff = fmaf(L2, xi, fmaf(bi, inv_aii, -L1));
     const bool clamp = (-diff > xi);
-    const float xnew = clamp ? 0.f : xi + diff;
-    const float term = fabsf(__fdividef(diff, xnew + 1e-15f));  // diff == 0 -> 0
-    tol = clamp ? ((xi != 0.f) ? 1.f : tol) : tol + term;
+    const float xsum = xi + diff;
+    float r;  // 1 / (x_new + 1e-15): single MUFU.RCP, evaluated on both paths so that no branch is needed
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(xsum + 1e-15f));
+    const float tol_clamp = (xi != 0.f) ? 1.f : tol;  // `tol = 1` only when x_i actually changes
+    const float tol_step = tol + fabsf(diff * r);     // diff == 0 adds exactly 0
+    tol = clamp ? tol_clamp : tol_step;
     const float m = clamp ? xi : -diff;
-    xi = xnew;
+    xi = clamp ? 0.f : xsum;
     return m;
 }
 
@@ -75,113 +78,135 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
     return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
 
-// Persistent variant with lane refill: columns converge after very different numbers of sweeps
-// (from ~30 to the 100-sweep cap once the factors have separated; early iterations hit the cap), so a lane whose column is done immediately
-// writes it back and claims the next unsolved column from a global counter instead of idling until
-// the slowest lane of its warp finishes. Columns are independent, so the result does not depend on
-// which lane solves which column. Row sums are taken afterwards by rowsum_partial_kernel.
+// Gram matrix and reciprocal diagonal of the current half-iteration, in constant memory: every thread
+// of the plain solver reads the same a[i][j] at the same time, so the loads go through the uniform
+// datapath (LDCU -> uniform registers feeding FFMA2 directly) and never touch the shared-memory
+// crossbar or the vector register file. Refreshed by cudaMemcpyToSymbolAsync before each launch.
+__constant__ __align__(16) float c_gram[64 * 64];
+__constant__ float c_inv_diag[64];
+
+// Persistent kernel with lane refill. Every lane solves NCL = 2 columns at a time (two independent
+// dependency chains per thread, and every Gram row fetched once feeds both). Columns converge after
+// very different numbers of sweeps (from ~30 up to the 100-sweep cap), so a slot whose column is done
+// writes it back and claims the next unsolved column from a global counter instead of idling until the
+// slowest lane of its warp finishes. Columns are independent, so the result does not depend on which
+// lane solves which column. Row sums are taken afterwards by rowsum_partial_kernel.
 template <int KP>
 __global__ void __launch_bounds__(NnlsCfg<KP>::THREADS, NnlsCfg<KP>::MIN_CTAS)
 nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
                  int splits, float* __restrict__ X,  // [ncol][KP] warm start in / solution out
-                 const float* __restrict__ gram_f,   // [KP][KP] float (symmetric)
-                 const float* __restrict__ inv_diag, // [KP]
                  const int64_t* __restrict__ colptr, int64_t ncol, int k, float L1, float L2,
                  unsigned long long* __restrict__ next_col,  // global work counter (zeroed by the host)
                  unsigned long long* __restrict__ stats)     // optional: [0] += sweeps, [1] += columns solved
 {
     constexpr int NT = NnlsCfg<KP>::THREADS;
-    __shared__ __align__(16) float sa[KP * KP];
-    __shared__ float sinv[KP];
-    __shared__ float sx[KP * NT];  // sx[i * NT + tid]
-
-    for (int t = threadIdx.x; t < KP * KP; t += NT) sa[t] = gram_f[t];
-    for (int t = threadIdx.x; t < KP; t += NT) sinv[t] = inv_diag[t];
-    __syncthreads();
+    constexpr int NCL = 2;
+    __shared__ float sx[NCL * KP * NT];  // sx[(s * KP + i) * NT + tid]
 
     const int lane = threadIdx.x & 31;
-    unsigned long long b2[KP / 2];  // b as packed FP32 pairs (the rank-1 update runs on FFMA2)
+    float2 b[NCL][KP / 2];  // right-hand sides as FP32 pairs (the rank-1 update runs on FFMA2)
+    int64_t col[NCL];
+    float tol[NCL];
+    int sweeps[NCL];
 #pragma unroll
-    for (int j2 = 0; j2 < KP / 2; ++j2) b2[j2] = 0ull;
-    int64_t col = -1;     // column being solved by this lane (-1: none)
+    for (int s = 0; s < NCL; ++s) {
+        col[s] = -1;
+        tol[s] = 1.f;
+        sweeps[s] = 0;
+#pragma unroll
+        for (int j2 = 0; j2 < KP / 2; ++j2) b[s][j2] = make_float2(0.f, 0.f);
+    }
     bool exhausted = false;  // the counter ran past ncol
-    float tol = 1.f;
-    int sweeps = 0;
     const float kf = (float)k;
-    const uint32_t sa_addr = smem_u32(sa);
+#pragma unroll
+    for (int j = 0; j < NCL * KP; ++j) sx[j * NT + threadIdx.x] = 0.f;
 
     while (true) {
-        // ---- retire finished columns and claim new ones (per lane; the warp takes this path together) ----
-        const bool finished = (col >= 0) && (sweeps >= NNLS_MAX_SWEEPS || !(tol / kf > 1e-8f));
-        bool need = (col < 0 || finished) && !exhausted;
-        if (finished) {
-            if (stats) { atomicAdd(&stats[0], (unsigned long long)sweeps); atomicAdd(&stats[1], 1ull); }
-            float4* xd = reinterpret_cast<float4*>(X + col * KP);
+        // ---- retire finished columns and claim new ones (per slot; the warp takes this path together) ----
 #pragma unroll
-            for (int j4 = 0; j4 < KP / 4; ++j4)
-                xd[j4] = make_float4(sx[(4 * j4 + 0) * NT + threadIdx.x], sx[(4 * j4 + 1) * NT + threadIdx.x],
-                                     sx[(4 * j4 + 2) * NT + threadIdx.x], sx[(4 * j4 + 3) * NT + threadIdx.x]);
-            col = -1;
-        }
-        while (__any_sync(0xffffffffu, need)) {
-            const uint32_t mask = __ballot_sync(0xffffffffu, need);
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(next_col, (unsigned long long)__popc(mask));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (need) {
-                const int64_t c = (int64_t)base + __popc(mask & ((1u << lane) - 1u));
-                if (c >= ncol) {
-                    exhausted = true;
-                    need = false;
-                } else if (colptr[c] != colptr[c + 1]) {  // empty columns are skipped (:340)
-                    float b[KP];
+        for (int s = 0; s < NCL; ++s) {
+            const bool finished = (col[s] >= 0) && (sweeps[s] >= NNLS_MAX_SWEEPS || !(tol[s] / kf > 1e-8f));
+            bool need = (col[s] < 0 || finished) && !exhausted;
+            if (finished) {
+                if (stats) { atomicAdd(&stats[0], (unsigned long long)sweeps[s]); atomicAdd(&stats[1], 1ull); }
+                float4* xd = reinterpret_cast<float4*>(X + col[s] * KP);
 #pragma unroll
-                    for (int j = 0; j < KP; ++j) b[j] = 0.f;
-                    for (int s = 0; s < splits; ++s) {
-                        const float4* src = reinterpret_cast<const float4*>(Bparts + ((int64_t)s * ncol + c) * KP);
+                for (int j4 = 0; j4 < KP / 4; ++j4)
+                    xd[j4] = make_float4(sx[(s * KP + 4 * j4 + 0) * NT + threadIdx.x], sx[(s * KP + 4 * j4 + 1) * NT + threadIdx.x],
+                                         sx[(s * KP + 4 * j4 + 2) * NT + threadIdx.x], sx[(s * KP + 4 * j4 + 3) * NT + threadIdx.x]);
+                col[s] = -1;
+                // an empty slot is made inert instead of being predicated off in the sweep: with b = 0 and
+                // x = 0 every coordinate step clamps at zero (diff = -L1 <= 0) and multiplies the update by 0
+#pragma unroll
+                for (int j2 = 0; j2 < KP / 2; ++j2) b[s][j2] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < KP; ++j) sx[(s * KP + j) * NT + threadIdx.x] = 0.f;
+            }
+            while (__any_sync(0xffffffffu, need)) {
+                const uint32_t mask = __ballot_sync(0xffffffffu, need);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(next_col, (unsigned long long)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (need) {
+                    const int64_t c = (int64_t)base + __popc(mask & ((1u << lane) - 1u));
+                    if (c >= ncol) {
+                        exhausted = true;
+                        need = false;
+                    } else if (colptr[c] != colptr[c + 1]) {  // empty columns are skipped (:340)
+#pragma unroll
+                        for (int j2 = 0; j2 < KP / 2; ++j2) b[s][j2] = make_float2(0.f, 0.f);
+                        for (int sp = 0; sp < splits; ++sp) {
+                            const float4* src = reinterpret_cast<const float4*>(Bparts + ((int64_t)sp * ncol + c) * KP);
+#pragma unroll
+                            for (int j4 = 0; j4 < KP / 4; ++j4) {
+                                const float4 v = src[j4];
+                                b[s][2 * j4].x += v.x; b[s][2 * j4].y += v.y; b[s][2 * j4 + 1].x += v.z; b[s][2 * j4 + 1].y += v.w;
+                            }
+                        }
+                        const float4* xs = reinterpret_cast<const float4*>(X + c * KP);
 #pragma unroll
                         for (int j4 = 0; j4 < KP / 4; ++j4) {
-                            const float4 v = src[j4];
-                            b[4 * j4 + 0] += v.x; b[4 * j4 + 1] += v.y; b[4 * j4 + 2] += v.z; b[4 * j4 + 3] += v.w;
+                            const float4 v = xs[j4];
+                            sx[(s * KP + 4 * j4 + 0) * NT + threadIdx.x] = v.x; sx[(s * KP + 4 * j4 + 1) * NT + threadIdx.x] = v.y;
+                            sx[(s * KP + 4 * j4 + 2) * NT + threadIdx.x] = v.z; sx[(s * KP + 4 * j4 + 3) * NT + threadIdx.x] = v.w;
                         }
-                    }
-#pragma unroll
-                    for (int j2 = 0; j2 < KP / 2; ++j2) b2[j2] = pack2(b[2 * j2], b[2 * j2 + 1]);
-                    const float4* xs = reinterpret_cast<const float4*>(X + c * KP);
-#pragma unroll
-                    for (int j4 = 0; j4 < KP / 4; ++j4) {
-                        const float4 v = xs[j4];
-                        sx[(4 * j4 + 0) * NT + threadIdx.x] = v.x; sx[(4 * j4 + 1) * NT + threadIdx.x] = v.y;
-                        sx[(4 * j4 + 2) * NT + threadIdx.x] = v.z; sx[(4 * j4 + 3) * NT + threadIdx.x] = v.w;
-                    }
-                    col = c;
-                    tol = 1.f;
-                    sweeps = 0;
-                    need = false;
-                }  // else: empty column, claim another one
+                        col[s] = c;
+                        tol[s] = 1.f;
+                        sweeps[s] = 0;
+                        need = false;
+                    }  // else: empty column, claim another one
+                }
             }
         }
-        const bool active = col >= 0;
-        if (!__any_sync(0xffffffffu, active)) break;
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < NCL; ++s) {
+            any = any || (col[s] >= 0);
+            tol[s] = 0.f;
+            ++sweeps[s];
+        }
+        if (!__any_sync(0xffffffffu, any)) break;
 
-        // ---- one sweep (src/singlet.cpp:231-248) for every lane that holds a column ----
-        tol = 0.f;
-        ++sweeps;
+        // ---- one sweep (src/singlet.cpp:231-248) for every slot that holds a column ----
 #pragma unroll
         for (int i = 0; i < KP; ++i) {
             if (i < k) {  // uniform
-                float xi = sx[i * NT + threadIdx.x], tl = tol;
-                const float bi = (i & 1) ? hi32(b2[i >> 1]) : lo32(b2[i >> 1]);
-                float mult = cd_step_nb(bi, sinv[i], xi, L1, L2, tl);
-                mult = active ? mult : 0.f;
-                tol = tl;
-                if (active) sx[i * NT + threadIdx.x] = xi;
+                float2 mm[NCL];
 #pragma unroll
-                for (int j4 = 0; j4 < KP / 4; ++j4) {
-                    unsigned long long a01, a23;
-                    asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a01), "=l"(a23) : "r"(sa_addr + (uint32_t)((i * KP + 4 * j4) * 4)));
-                    ffma2_bcast(b2[2 * j4 + 0], a01, mult);
-                    ffma2_bcast(b2[2 * j4 + 1], a23, mult);
+                for (int s = 0; s < NCL; ++s) {
+                    float xi = sx[(s * KP + i) * NT + threadIdx.x], tl = tol[s];
+                    const float bi = (i & 1) ? b[s][i >> 1].y : b[s][i >> 1].x;
+                    const float mult = cd_step_nb(bi, c_inv_diag[i], xi, L1, L2, tl);
+                    tol[s] = tl;
+                    sx[(s * KP + i) * NT + threadIdx.x] = xi;
+                    mm[s] = make_float2(mult, mult);
+                }
+                const float2* ai = reinterpret_cast<const float2*>(c_gram + i * KP);
+#pragma unroll
+                for (int j2 = 0; j2 < KP / 2; ++j2) {
+                    const float2 a2 = ai[j2];
+#pragma unroll
+                    for (int s = 0; s < NCL; ++s) b[s][j2] = __ffma2_rn(a2, mm[s], b[s][j2]);
                 }
             }
         }
