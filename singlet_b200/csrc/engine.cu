@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -99,6 +100,11 @@ struct sgl_handle {
     DevBuf<int64_t> counts;
     DevBuf<unsigned long long> workctr;
     double* pinned = nullptr;  // 64 doubles of pinned host scratch
+    // pinned staging ring for uploads: host threads pack {int32 row, float value} records into it
+    static constexpr int NSTAGE = 3;
+    uint2* stage[NSTAGE] = {nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev[NSTAGE] = {nullptr, nullptr, nullptr};
+    size_t stage_records = 0;
     // optional per-kernel-kind event timing (bench.py's roofline numbers are measured live with it)
     bool profiling = false;
     struct Span { int kind; cudaEvent_t a, b; int64_t bytes; };
@@ -243,24 +249,33 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
         matrix_release(m);
         return fail(SGL_ENOMEM, "matrix upload: cudaMalloc failed for %lld non-zeros", (long long)nnz);
     }
-    // staging: pieces of at most PIECE non-zeros go through temporary device buffers
-    const int64_t PIECE = 32ll << 20;
-    int32_t* d_idx = nullptr;
-    double* d_val = nullptr;
+    // Records are packed on the host: several threads convert the dgCMatrix slots (int32 i, double x)
+    // of a piece into {int32 row, float value} records inside a pinned staging buffer, which is then
+    // copied straight into m->rec while the threads fill the next buffer (3-deep ring). This moves
+    // 8 B per non-zero over PCIe instead of 12 B and keeps the copy engine busy.
+    const size_t PIECE = (size_t)8 << 20;  // records per staging buffer (64 MB)
+    if (!h->stage[0]) {
+        for (int q = 0; q < sgl_handle::NSTAGE; ++q) {
+            if (cudaMallocHost(&h->stage[q], PIECE * sizeof(uint2)) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->stage_ev[q], cudaEventDisableTiming) != cudaSuccess) {
+                matrix_release(m);
+                return fail(SGL_ENOMEM, "matrix upload: pinned staging allocation failed");
+            }
+        }
+        h->stage_records = PIECE;
+    }
     int32_t* d_p = nullptr;
     int64_t max_cols = 0;
     for (int q = 0; q < n_chunks; ++q) max_cols = chunks[q].ncol > max_cols ? chunks[q].ncol : max_cols;
-    const int64_t piece = nnz < PIECE ? (nnz > 0 ? nnz : 1) : PIECE;
-    if (cudaMalloc(&d_idx, sizeof(int32_t) * piece) != cudaSuccess || cudaMalloc(&d_val, sizeof(double) * piece) != cudaSuccess ||
-        cudaMalloc(&d_p, sizeof(int32_t) * (size_t)(max_cols + 1)) != cudaSuccess) {
-        if (d_idx) cudaFree(d_idx);
-        if (d_val) cudaFree(d_val);
-        if (d_p) cudaFree(d_p);
+    if (cudaMalloc(&d_p, sizeof(int32_t) * (size_t)(max_cols + 1)) != cudaSuccess) {
         matrix_release(m);
         return fail(SGL_ENOMEM, "matrix upload: staging cudaMalloc failed");
     }
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n_threads = (int)(hw == 0 ? 4 : (hw > 12 ? 12 : hw));
     int rc = SGL_OK;
     int64_t col_off = 0, nnz_off = 0;
+    int64_t piece_no = 0;
     for (int q = 0; q < n_chunks && rc == SGL_OK; ++q) {
         const sgl_csc& c = chunks[q];
         const int64_t cn = c.p[c.ncol];
@@ -268,14 +283,38 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
         const int last = (q == n_chunks - 1) ? 1 : 0;
         colptr_from_p32_kernel<<<blocks_for(c.ncol + 1, 256), 256, 0, h->stream>>>(d_p, c.ncol, nnz_off, m->colptr + col_off, last);
         ++h->launches;
-        for (int64_t o = 0; o < cn; o += piece) {
-            const int64_t len = (cn - o) < piece ? (cn - o) : piece;
-            cudaMemcpyAsync(d_idx, c.i + o, sizeof(int32_t) * (size_t)len, cudaMemcpyHostToDevice, h->stream);
-            cudaMemcpyAsync(d_val, c.x + o, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, h->stream);
-            pack_records_kernel<<<blocks_for(len, 256), 256, 0, h->stream>>>(d_idx, d_val, len, m->rec + nnz_off + o);
-            ++h->launches;
+        cudaStreamSynchronize(h->stream);  // d_p is reused by the next chunk
+        for (int64_t o = 0; o < cn; o += (int64_t)PIECE, ++piece_no) {
+            const int64_t len = (cn - o) < (int64_t)PIECE ? (cn - o) : (int64_t)PIECE;
+            const int sidx = (int)(piece_no % sgl_handle::NSTAGE);
+            if (piece_no >= sgl_handle::NSTAGE) cudaEventSynchronize(h->stage_ev[sidx]);  // buffer free again
+            uint2* dstbuf = h->stage[sidx];
+            const int32_t* si = c.i + o;
+            const double* sx = c.x + o;
+            auto work = [dstbuf, si, sx](int64_t b, int64_t e) {
+                for (int64_t t = b; t < e; ++t) {
+                    const float v = (float)sx[t];
+                    uint32_t bits;
+                    std::memcpy(&bits, &v, 4);
+                    dstbuf[t] = make_uint2((uint32_t)si[t], bits);
+                }
+            };
+            const int nt = len < (1 << 16) ? 1 : n_threads;
+            if (nt == 1) {
+                work(0, len);
+            } else {
+                std::vector<std::thread> pool;
+                const int64_t per = (len + nt - 1) / nt;
+                for (int w = 0; w < nt; ++w) {
+                    const int64_t b = w * per, e = (b + per) < len ? (b + per) : len;
+                    if (b < e) pool.emplace_back(work, b, e);
+                }
+                for (auto& th : pool) th.join();
+            }
+            cudaMemcpyAsync(m->rec + nnz_off + o, dstbuf, sizeof(uint2) * (size_t)len, cudaMemcpyHostToDevice, h->stream);
+            cudaEventRecord(h->stage_ev[sidx], h->stream);
         }
-        if (cudaGetLastError() != cudaSuccess) rc = fail(SGL_ECUDA, "matrix upload: copy/pack failed");
+        if (cudaGetLastError() != cudaSuccess) rc = fail(SGL_ECUDA, "matrix upload: copy failed");
         col_off += c.ncol;
         nnz_off += cn;
     }
@@ -284,8 +323,6 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
         cudaMemcpyAsync(m->colptr, &zero, sizeof(int64_t), cudaMemcpyHostToDevice, h->stream);
     }
     cudaError_t es = cudaStreamSynchronize(h->stream);
-    cudaFree(d_idx);
-    cudaFree(d_val);
     cudaFree(d_p);
     if (rc == SGL_OK && es != cudaSuccess) rc = fail(SGL_ECUDA, "matrix upload: %s", cudaGetErrorString(es));
     if (rc != SGL_OK) {
@@ -856,6 +893,10 @@ int sgl_destroy(sgl_handle* h) {
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (int q = 0; q < sgl_handle::NSTAGE; ++q) {
+        if (h->stage[q]) cudaFreeHost(h->stage[q]);
+        if (h->stage_ev[q]) cudaEventDestroy(h->stage_ev[q]);
+    }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return SGL_OK;
