@@ -259,3 +259,54 @@ def test_error_paths(handle):
         api.c_nmf(A, A, 1e-4, 2, False, 0, 0, 0, 0, 0, synth.w_init(4, 300))
     with pytest.raises(SingletCudaError):  # trace_test_mse = 0 divides by zero in the reference
         api.c_ard_nmf(A, At, 1e-4, 2, False, 0, 0, 0, synth.w_init(4, 300), 1, 20, 1e-3, 0)
+
+
+def test_masked_rank_above_64_generic_kernel(handle, oracle):
+    """k > 64 takes the generic shared-memory masked solver (KP = 128) and the big plain solver."""
+    from singlet_b200 import api, synth
+
+    m, n, k = 260, 150, 70
+    A, At = _mk(m, n, 0.3, seed=12)
+    w0 = synth.w_init(k, m, seed=1)
+    dev = api.c_ard_nmf(A, At, 0.0, 2, False, 0.01, 0.0, 0, w0, 123, 10, 10.0, 1)
+    ref = oracle.ard_nmf(A, At, w0, 123, 10, tol=0.0, maxit=2, L1=0.01, L2=0.0, overfit_threshold=10.0, trace_test_mse=1)
+    assert list(dev["iter"]) == list(ref["iter"])
+    assert np.allclose(dev["test_mse"], ref["test_mse"], rtol=1e-3)
+    devp = api.c_nmf(A, At, 0.0, 2, False, 0.01, 0.01, 0.0, 0.0, 0, w0)
+    refp = oracle.nmf(A, At, w0, tol=0.0, maxit=2)
+    tr_d, tr_r = oracle.mse_train(A, devp["w"], devp["d"], devp["h"]), oracle.mse_train(A, refp["w"], refp["d"], refp["h"])
+    assert abs(tr_d - tr_r) <= 1e-3 * tr_r
+
+
+def test_r_level_api_on_gpu(handle, oracle):
+    """run_nmf / cross_validate_nmf / ard_nmf (R/run_nmf.R, R/cross_validate_nmf.R, R/ard_nmf.R) end to end:
+    same RNG stream as R (set.seed), same sorting by d, same CV table columns."""
+    from singlet_b200 import api
+    from singlet_b200.rrng import RRng
+
+    m, n = 400, 300
+    A, At = _mk(m, n, 0.1, seed=33)
+    api.set_seed(123)
+    model = api.run_nmf(A, 5, maxit=6, tol=0.0, verbose=False)
+    assert model["w"].shape == (m, 5) and model["h"].shape == (5, n) and np.all(np.diff(model["d"]) <= 0)
+    w0 = RRng(123).matrix_runif(5, m)  # what matrix(runif(m * k), k, m) draws after set.seed(123)
+    ref = oracle.nmf(A, At, w0, tol=0.0, maxit=6)
+    order = np.argsort(-ref["d"], kind="stable")
+    assert min_factor_cor(ref["w"][order], model["w"].T) >= COR_MIN
+    assert np.allclose(model["d"], ref["d"][order], rtol=5e-3)
+
+    api.set_seed(123)
+    df = api.cross_validate_nmf(A, [2, 3, 4], n_replicates=2, maxit=10, verbose=0, trace_test_mse=5)
+    assert list(df.columns) == ["k", "rep", "test_error", "iter", "tol"]
+    assert set(df["k"]) == {2, 3, 4} and set(df["rep"]) == {1, 2}
+    r = RRng(123)
+    w_init = [r.matrix_runif(4, m) for _ in range(2)]
+    seed1 = abs(r.dot_random_seed(4))  # abs(.Random.seed[[3 + 1]])
+    cm = oracle.ard_nmf(A, At, w_init[0][:3, :], seed1, 20, tol=1e-4, maxit=10, trace_test_mse=5)
+    got = df[(df["k"] == 3) & (df["rep"] == 1)]
+    assert list(got["iter"]) == list(cm["iter"]) and np.allclose(got["test_error"], cm["test_mse"], rtol=MSE_RTOL)
+    assert 2 <= api.GetBestRank(df) <= 4
+
+    api.set_seed(7)
+    am = api.ard_nmf(A, k_init=2, k_max=6, maxit=6, verbose=0)
+    assert am["w"].shape[0] == m and 2 <= am["w"].shape[1] <= 6 and len(am["cv_data"]) > 0
