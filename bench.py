@@ -168,7 +168,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     base_cfg = {"workload": cfg["name"], "m_genes": m, "n_cells": n, "density": dens, "k": k, "L1": L1, "L2": L2,
-                "tol": 0.0, "parallelism": f"cells/genes sharded over {world} GPU(s)",
+                "tol": 0.0, "parallelism": f"cells sharded over {world} GPU(s); W-update RHS reduce-scattered, W all-gathered (layout B)",
                 "cache_policy": "inputs larger than L2 (A and At streams are GBs per half-iteration)"}
 
     if args.impl == "reference":
@@ -212,12 +212,14 @@ def main():
     c0, c1, _ = shard_bounds(n, world, rank)
     g0, g1, _ = shard_bounds(m, world, rank)
     t_gen = time.perf_counter()
+    # layout "B" (sharded.py): this rank's cells for the H update, and the transpose of the SAME cell block
+    # (local cells x all genes) for its partial W-update right-hand sides
     A_sh = be.synth(m, n, dens, synth.DATA_SEED, 0, c0, c1 - c0, table)
-    At_sh = be.synth(m, n, dens, synth.DATA_SEED, 1, g0, g1 - g0, table)
+    At_sh = be.synth_block(m, n, dens, synth.DATA_SEED, 1, 0, m, c0, c1 - c0, table)
     be.synchronize()
     t_gen = time.perf_counter() - t_gen
     nnz_A, nnz_At = be.matrix_info(A_sh)[2], be.matrix_info(At_sh)[2]
-    fit = ShardedNMF(be, m, n, k, A_sh, At_sh, rank, world, group)
+    fit = ShardedNMF(be, m, n, k, A_sh, At_sh, rank, world, group, layout="B")
     fit.set_w(synth.w_init(k, m))
 
     def barrier():
@@ -277,7 +279,7 @@ def main():
                "data": "synthetic (device-generated, bit-identical to singlet_b200/synth.py)",
                "config": dict(base_cfg, nnz=nnz_total, generate_s=round(t_gen, 3), final_tol=tol),
                "gpu_launches": total_launches, "clocks": clocks,
-               "roofline": {"bound": "hbm", "kernel": "spmm_tiles_kernel<32> (mean of the H-update and W-update launches, rank 0)",
+               "roofline": {"bound": "hbm", "kernel": "spmm_stream_kernel<32> (mean of the H-update and W-update launches, rank 0)",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes,
                             "ms_per_launch": per_launch_ms, "launches_timed": spmm_cnt},

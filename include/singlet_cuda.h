@@ -129,6 +129,13 @@ int sgl_matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl_ma
  * orientation 1: columns = genes [col0, col0+ncol) of its transpose. values_table: 8 floats. */
 int sgl_matrix_synth(sgl_handle* h, int64_t m_genes, int64_t n_cells, double density, uint64_t data_seed,
                      int orientation, int64_t col0, int64_t ncol, const float* values_table, sgl_matrix** out);
+/* Same, restricted to the rows [row0, row0 + nrows) of that orientation and re-based to 0 (a rank's block of the
+ * transpose over its own cells only). */
+int sgl_matrix_synth_block(sgl_handle* h, int64_t m_genes, int64_t n_cells, double density, uint64_t data_seed,
+                           int orientation, int64_t col0, int64_t ncol, int64_t row0, int64_t nrows,
+                           const float* values_table, sgl_matrix** out);
+/* Copy the column pointers (int64[ncol + 1]) into a caller-owned DEVICE buffer (stream-ordered). */
+int sgl_matrix_colptr(sgl_handle* h, const sgl_matrix* m, int64_t* dst_device);
 int sgl_matrix_free(sgl_handle* h, sgl_matrix* m);
 int sgl_matrix_info(const sgl_matrix* m, int64_t* nrow, int64_t* ncol, int64_t* nnz);
 /* Copy back to host in dgCMatrix form (p may be int32 only if nnz < 2^31). Synchronises. */
@@ -149,6 +156,14 @@ int sgl_dev_gram_jitter(sgl_handle* h, int k, double* gram);
  * (the local part of `scale`'s d, without the 1e-15). */
 int sgl_dev_update(sgl_handle* h, const sgl_matrix* X, const float* F_in, float* F_out, int k, const double* gram,
                    double L1, double L2, double* rowsum);
+
+/* The two halves of sgl_dev_update, for layouts where the right-hand sides are summed across GPUs before the
+ * solve: sgl_dev_rhs writes B[ncol][KP] = F_in . X (float, device); sgl_dev_solve runs the NNLS on B for `ncol`
+ * columns. colptr_like is any int64[ncol + 1] device array with colptr_like[c] == colptr_like[c+1] exactly for the
+ * columns that are empty in the GLOBAL matrix (they are skipped like src/singlet.cpp:340). */
+int sgl_dev_rhs(sgl_handle* h, const sgl_matrix* X, const float* F_in, int k, float* B_out);
+int sgl_dev_solve(sgl_handle* h, const float* B, const int64_t* colptr_like, int64_t ncol, float* F_out, int k,
+                  const double* gram, double L1, double L2, double* rowsum);
 
 /* scale (src/singlet.cpp:219-225): F[c][f] /= d[f]; d is double[KP] on the device (already
  * all-reduced and with the 1e-15 added -- see sgl_dev_finish_d). */

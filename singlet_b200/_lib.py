@@ -67,6 +67,8 @@ SYMBOLS = [
     ("sgl_padded_rank", _i32, [_i32]),
     ("sgl_matrix_upload", _i32, [_vp, _vp, _i32, C.POINTER(_vp)]),
     ("sgl_matrix_synth", _i32, [_vp, _i64, _i64, _dbl, _u64, _i32, _i64, _i64, _vp, C.POINTER(_vp)]),
+    ("sgl_matrix_synth_block", _i32, [_vp, _i64, _i64, _dbl, _u64, _i32, _i64, _i64, _i64, _i64, _vp, C.POINTER(_vp)]),
+    ("sgl_matrix_colptr", _i32, [_vp, _vp, _vp]),
     ("sgl_matrix_free", _i32, [_vp, _vp]),
     ("sgl_matrix_info", _i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     ("sgl_matrix_download", _i32, [_vp, _vp, _vp, _vp, _vp]),
@@ -75,6 +77,8 @@ SYMBOLS = [
     ("sgl_dev_gram", _i32, [_vp, _vp, _i32, _i64, _vp, _i32]),
     ("sgl_dev_gram_jitter", _i32, [_vp, _i32, _vp]),
     ("sgl_dev_update", _i32, [_vp, _vp, _vp, _vp, _i32, _vp, _dbl, _dbl, _vp]),
+    ("sgl_dev_rhs", _i32, [_vp, _vp, _vp, _i32, _vp]),
+    ("sgl_dev_solve", _i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _dbl, _dbl, _vp]),
     ("sgl_dev_finish_d", _i32, [_vp, _i32, _vp]),
     ("sgl_dev_scale", _i32, [_vp, _vp, _i32, _i64, _vp]),
     ("sgl_dev_cor_sums", _i32, [_vp, _vp, _vp, _i32, _i64, _vp]),

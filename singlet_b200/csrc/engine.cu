@@ -442,33 +442,35 @@ static int launch_spmm(sgl_handle* h, const sgl_matrix* X, const uint2* stream, 
     return SGL_OK;
 }
 
-// predict / predict_mask for all columns of X (src/singlet.cpp:333-347, 436-466)
-static int dev_update(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask, const float* F_in, float* F_out, int k,
-                      const double* gram, double L1, double L2, double* rowsum) {
+// right-hand sides b = F_in . X[:, c] for all columns of X (src/singlet.cpp:341-343) -> h->bparts as
+// [splits][ncol][KP] partial sums over row-tile ranges (summed in fixed order by the solver)
+static int dev_rhs(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask, const float* F_in, int k, int* splits_out) {
     sgl_matrix* X = const_cast<sgl_matrix*>(Xc);
     const int KPV = kp_of(k);
-    if (X->ncol == 0) {
-        SGL_CUDA(cudaMemsetAsync(rowsum, 0, sizeof(double) * KPV, h->stream));
-        return SGL_OK;
-    }
     const TileIndex* ti = nullptr;
     SGL_TRY(get_tiles(h, X, KPV, &ti));
-    SGL_TRY(h->gram_f.ensure((size_t)KPV * KPV));
-    SGL_TRY(h->gram_f_nojit.ensure((size_t)KPV * KPV));
-    SGL_TRY(h->inv_diag.ensure((size_t)KPV));
-    gram_finish_kernel<<<1, 256, 0, h->stream>>>(gram, k, KPV, h->gram_f.p, h->gram_f_nojit.p, h->inv_diag.p);
-    LAUNCH_CHECK(h);
 
     // split the tile range when there are too few column groups to fill the chip
     int cols_per_cta = 0;
     DISPATCH_KP(KPV, cols_per_cta = SpmmCfg<KP>::COLS_PER_CTA);
     const int64_t groups = (X->ncol + cols_per_cta - 1) / cols_per_cta;
+    // Split the tile range when there are too few column groups to fill the chip. Cost model: the grid
+    // runs in ceil(ctas / SMs) waves of ceil(n_tiles / splits) tiles each; take the cheapest split count
+    // (ties -> fewer splits, i.e. fewer partial buffers).
     int splits = 1;
-    if (groups < 2 * h->sm_count) {
-        splits = (int)((4 * h->sm_count + groups - 1) / groups);
-        if (splits > ti->n_tiles) splits = ti->n_tiles;
-        if (splits > 16) splits = 16;
-        if (splits < 1) splits = 1;
+    {
+        const int64_t ctas1 = groups > 0 ? groups : 1;  // CTAs per split
+        const int max_splits = ti->n_tiles < 32 ? ti->n_tiles : 32;
+        double best = 1e300;
+        for (int sp = 1; sp <= (max_splits > 0 ? max_splits : 1); ++sp) {
+            const int64_t waves = (ctas1 * sp + h->sm_count - 1) / h->sm_count;
+            const int tps = (ti->n_tiles + sp - 1) / sp;
+            const double cost = (double)waves * ((double)tps + 1.5);  // +1.5 tiles of pipeline fill per CTA
+            if (cost < best * 0.999) {
+                best = cost;
+                splits = sp;
+            }
+        }
     }
     const int tiles_per_split = (ti->n_tiles + splits - 1) / splits;
     splits = (ti->n_tiles + tiles_per_split - 1) / tiles_per_split;
@@ -491,8 +493,21 @@ static int dev_update(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask,
         ProfScope ps(h, PK_SPMM, 8 * X->nnz + 4 * (X->ncol + 1) + 4ll * k * X->nrow + 4ll * k * X->ncol);
         DISPATCH_KP(KPV, SGL_TRY(launch_spmm<KP>(h, X, rec, *ti, F_in, h->bparts.p, splits, tiles_per_split)));
     }
-    ProfScope ps_nnls(h, PK_NNLS, 0);
+    *splits_out = splits;
+    return SGL_OK;
+}
 
+// coordinate-descent solves for `ncol` columns (src/singlet.cpp:229-250 via :345 / :464). Bparts is
+// [splits][ncol][KP]; colptr only tells which columns are empty (they are skipped, :340/:444).
+static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64_t* colptr, int64_t ncol, const sgl_mask* mask,
+                     const float* F_in, float* F_out, int k, const double* gram, double L1, double L2, double* rowsum) {
+    const int KPV = kp_of(k);
+    SGL_TRY(h->gram_f.ensure((size_t)KPV * KPV));
+    SGL_TRY(h->gram_f_nojit.ensure((size_t)KPV * KPV));
+    SGL_TRY(h->inv_diag.ensure((size_t)KPV));
+    gram_finish_kernel<<<1, 256, 0, h->stream>>>(gram, k, KPV, h->gram_f.p, h->gram_f_nojit.p, h->inv_diag.p);
+    LAUNCH_CHECK(h);
+    ProfScope ps_nnls(h, PK_NNLS, 0);
     int64_t n_parts = 0;
     if (!mask) {
         if (KPV <= 64) {
@@ -510,44 +525,50 @@ static int dev_update(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask,
             SGL_CUDA(cudaMemcpyToSymbolAsync(c_gram, h->gram_f.p, sizeof(float) * KPV * KPV, 0, cudaMemcpyDeviceToDevice, h->stream));
             SGL_CUDA(cudaMemcpyToSymbolAsync(c_inv_diag, h->inv_diag.p, sizeof(float) * KPV, 0, cudaMemcpyDeviceToDevice, h->stream));
             switch (KPV) {
-#define NNLS_CASE(KPC)                                                                                              \
-    case KPC: {                                                                                                     \
+#define NNLS_LAUNCH(KPC, NTC, NCLC)                                                                                  \
+    {                                                                                                               \
         static int occ = 0;                                                                                         \
-        if (!occ && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nnls_cols_kernel<KPC>, NnlsCfg<KPC>::THREADS, 0) != cudaSuccess) occ = NnlsCfg<KPC>::MIN_CTAS; \
+        if (!occ && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nnls_cols_kernel<KPC, NTC, NCLC>, NTC, 0) != cudaSuccess) occ = 1; \
         int64_t ctas = (int64_t)h->sm_count * (occ > 0 ? occ : 1);                                                  \
-        const int64_t want = (X->ncol + NnlsCfg<KPC>::THREADS - 1) / NnlsCfg<KPC>::THREADS;                          \
+        const int64_t want = (ncol + (NTC) * (NCLC) - 1) / ((NTC) * (NCLC));                                      \
         if (ctas > want) ctas = want;                                                                               \
-        nnls_cols_kernel<KPC><<<(unsigned)ctas, NnlsCfg<KPC>::THREADS, 0, h->stream>>>(                              \
-            h->bparts.p, splits, F_out, X->colptr, X->ncol, k, (float)L1, (float)L2, h->workctr.p, dbg_stats ? h->workctr.p + 2 : nullptr); \
-    } break;
+        nnls_cols_kernel<KPC, NTC, NCLC><<<(unsigned)ctas, NTC, 0, h->stream>>>(                                      \
+            Bparts, splits, F_out, colptr, ncol, k, (float)L1, (float)L2, h->workctr.p, dbg_stats ? h->workctr.p + 2 : nullptr); \
+    }
+#define NNLS_CASE(KPC)                                                                                              \
+    case KPC:                                                                                                       \
+        if (ncol >= (int64_t)h->sm_count * NnlsCfg<KPC>::THREADS * 2) NNLS_LAUNCH(KPC, NnlsCfg<KPC>::THREADS, 2)   \
+        else NNLS_LAUNCH(KPC, 32, 1)                                                                                \
+        break;
                 NNLS_CASE(4) NNLS_CASE(8) NNLS_CASE(16) NNLS_CASE(32) NNLS_CASE(64)
                 default: break;
+#undef NNLS_LAUNCH
 #undef NNLS_CASE
             }
             LAUNCH_CHECK(h);
             // row sums of the new solution (the local part of scale's d)
-            n_parts = (X->ncol + 255) / 256;
+            n_parts = (ncol + 255) / 256;
             if (n_parts > 2 * h->sm_count) n_parts = 2 * h->sm_count;
             SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
-            DISPATCH_KP(KPV, (rowsum_partial_kernel<KP><<<(unsigned)n_parts, 256, 0, h->stream>>>(F_out, X->ncol, h->part.p)));
+            DISPATCH_KP(KPV, (rowsum_partial_kernel<KP><<<(unsigned)n_parts, 256, 0, h->stream>>>(F_out, ncol, h->part.p)));
         } else {
-            n_parts = (X->ncol + 31) / 32;
+            n_parts = (ncol + 31) / 32;
             SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
             const size_t smem = 2 * (size_t)KPV * 32 * sizeof(float);
-            nnls_cols_big_kernel<<<(unsigned)n_parts, 32, smem, h->stream>>>(h->bparts.p, splits, F_out, h->gram_f.p, h->inv_diag.p,
-                                                                            X->colptr, X->ncol, k, KPV, (float)L1, (float)L2, h->part.p);
+            nnls_cols_big_kernel<<<(unsigned)n_parts, 32, smem, h->stream>>>(Bparts, splits, F_out, h->gram_f.p, h->inv_diag.p,
+                                                                            colptr, ncol, k, KPV, (float)L1, (float)L2, h->part.p);
         }
         LAUNCH_CHECK(h);
     } else {
         if (KPV <= 64) {
             const int warps = 4;
-            n_parts = (X->ncol + warps - 1) / warps;
+            n_parts = (ncol + warps - 1) / warps;
             SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
             switch (KPV) {
 #define MASKED_CASE(KPC)                                                                                            \
     case KPC:                                                                                                       \
         nnls_masked_kernel<KPC><<<(unsigned)n_parts, MaskedCfg<KPC>::WARPS * 32, 0, h->stream>>>(                    \
-            h->bparts.p, splits, F_out, h->gram_f_nojit.p, F_in, X->colptr, mask->mptr, mask->mrec, X->ncol, k, (float)L1, \
+            Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, mask->mptr, mask->mrec, ncol, k, (float)L1, \
             (float)L2, h->part.p);                                                                                  \
         break;
                 MASKED_CASE(4) MASKED_CASE(8) MASKED_CASE(16) MASKED_CASE(32) MASKED_CASE(64)
@@ -555,7 +576,7 @@ static int dev_update(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask,
 #undef MASKED_CASE
             }
         } else {
-            n_parts = X->ncol;
+            n_parts = ncol;
             SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
             const size_t smem = ((size_t)KPV * (KPV + 1) + 3 * (size_t)KPV) * sizeof(float);
             static bool attr_done = false;
@@ -563,14 +584,26 @@ static int dev_update(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask,
                 SGL_CUDA(cudaFuncSetAttribute(nnls_masked_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                 attr_done = true;
             }
-            nnls_masked_big_kernel<<<(unsigned)n_parts, 32, smem, h->stream>>>(h->bparts.p, splits, F_out, h->gram_f_nojit.p, F_in,
-                                                                              X->colptr, mask->mptr, mask->mrec, X->ncol, k, KPV,
+            nnls_masked_big_kernel<<<(unsigned)n_parts, 32, smem, h->stream>>>(Bparts, splits, F_out, h->gram_f_nojit.p, F_in,
+                                                                              colptr, mask->mptr, mask->mrec, ncol, k, KPV,
                                                                               (float)L1, (float)L2, h->part.p);
         }
         LAUNCH_CHECK(h);
     }
     SGL_TRY(reduce_partials(h, h->part.p, n_parts, KPV, rowsum));
     return SGL_OK;
+}
+
+// predict / predict_mask for all columns of X (src/singlet.cpp:333-347, 436-466)
+static int dev_update(sgl_handle* h, const sgl_matrix* X, const sgl_mask* mask, const float* F_in, float* F_out, int k,
+                      const double* gram, double L1, double L2, double* rowsum) {
+    if (X->ncol == 0) {
+        SGL_CUDA(cudaMemsetAsync(rowsum, 0, sizeof(double) * kp_of(k), h->stream));
+        return SGL_OK;
+    }
+    int splits = 1;
+    SGL_TRY(dev_rhs(h, X, mask, F_in, k, &splits));
+    return dev_solve(h, h->bparts.p, splits, X->colptr, X->ncol, mask, F_in, F_out, k, gram, L1, L2, rowsum);
 }
 
 static int dev_finish_d(sgl_handle* h, int k, double* d) {
@@ -1134,7 +1167,17 @@ int sgl_matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl_ma
 
 int sgl_matrix_synth(sgl_handle* h, int64_t m_genes, int64_t n_cells, double density, uint64_t data_seed, int orientation,
                      int64_t col0, int64_t ncol, const float* values_table, sgl_matrix** out) {
+    return sgl_matrix_synth_block(h, m_genes, n_cells, density, data_seed, orientation, col0, ncol, 0,
+                                  orientation == 0 ? m_genes : n_cells, values_table, out);
+}
+
+int sgl_matrix_synth_block(sgl_handle* h, int64_t m_genes, int64_t n_cells, double density, uint64_t data_seed, int orientation,
+                           int64_t col0, int64_t ncol, int64_t row0, int64_t nrows, const float* values_table, sgl_matrix** out) {
     if (!h || !out || !values_table) return fail(SGL_EINVAL, "NULL argument");
+    {
+        const int64_t total_rows = orientation == 0 ? m_genes : n_cells;
+        if (row0 < 0 || nrows < 1 || row0 + nrows > total_rows) return fail(SGL_EINVAL, "synth: row range out of bounds");
+    }
     if (m_genes < 1 || m_genes > 0x7fffffffLL || n_cells < 1 || n_cells > 0xffffffffLL || density <= 0 || density > 0.5)
         return fail(SGL_EINVAL, "synth: bad shape or density");
     const int64_t total_cols = orientation == 0 ? n_cells : m_genes;
@@ -1153,7 +1196,7 @@ int sgl_matrix_synth(sgl_handle* h, int64_t m_genes, int64_t n_cells, double den
     sp.q32 = (uint32_t)std::floor(q + 0.5);
     for (int t = 0; t < 8; ++t) sp.table[t] = values_table[t];
     sgl_matrix* m = new sgl_matrix();
-    m->nrow = orientation == 0 ? m_genes : n_cells;
+    m->nrow = nrows;
     m->ncol = ncol;
     int rc = SGL_OK;
     do {
@@ -1164,7 +1207,7 @@ int sgl_matrix_synth(sgl_handle* h, int64_t m_genes, int64_t n_cells, double den
         }
         const unsigned grid = blocks_for(ncol, 8);
         if (ncol > 0) {
-            synth_kernel<0><<<grid, 256, 0, h->stream>>>(sp, orientation, col0, ncol, h->counts.p, nullptr, nullptr);
+            synth_kernel<0><<<grid, 256, 0, h->stream>>>(sp, orientation, col0, ncol, row0, nrows, h->counts.p, nullptr, nullptr);
             ++h->launches;
         }
         exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->counts.p, ncol, m->colptr);
@@ -1182,7 +1225,7 @@ int sgl_matrix_synth(sgl_handle* h, int64_t m_genes, int64_t n_cells, double den
             break;
         }
         if (ncol > 0) {
-            synth_kernel<1><<<grid, 256, 0, h->stream>>>(sp, orientation, col0, ncol, nullptr, m->colptr, m->rec);
+            synth_kernel<1><<<grid, 256, 0, h->stream>>>(sp, orientation, col0, ncol, row0, nrows, nullptr, m->colptr, m->rec);
             ++h->launches;
         }
         e = cudaStreamSynchronize(h->stream);
@@ -1206,6 +1249,12 @@ int sgl_matrix_info(const sgl_matrix* m, int64_t* nrow, int64_t* ncol, int64_t* 
     if (nrow) *nrow = m->nrow;
     if (ncol) *ncol = m->ncol;
     if (nnz) *nnz = m->nnz;
+    return SGL_OK;
+}
+int sgl_matrix_colptr(sgl_handle* h, const sgl_matrix* m, int64_t* dst_device) {
+    if (!h || !m || !dst_device) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(set_device(h));
+    SGL_CUDA(cudaMemcpyAsync(dst_device, m->colptr, sizeof(int64_t) * (size_t)(m->ncol + 1), cudaMemcpyDeviceToDevice, h->stream));
     return SGL_OK;
 }
 int sgl_matrix_download(sgl_handle* h, const sgl_matrix* m, int32_t* p, int32_t* i, double* x) {
@@ -1274,6 +1323,30 @@ int sgl_dev_update(sgl_handle* h, const sgl_matrix* X, const float* F_in, float*
     SGL_TRY(check_k(k));
     SGL_TRY(set_device(h));
     return dev_update(h, X, nullptr, F_in, F_out, k, gram, L1, L2, rowsum);
+}
+int sgl_dev_rhs(sgl_handle* h, const sgl_matrix* X, const float* F_in, int k, float* B_out) {
+    if (!h || !X || !F_in || !B_out) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    const int KPV = kp_of(k);
+    if (X->ncol == 0) return SGL_OK;
+    int splits = 1;
+    SGL_TRY(dev_rhs(h, X, nullptr, F_in, k, &splits));
+    const int64_t n = X->ncol * KPV;
+    sum_splits_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->bparts.p, splits, n, B_out);
+    LAUNCH_CHECK(h);
+    return SGL_OK;
+}
+int sgl_dev_solve(sgl_handle* h, const float* B, const int64_t* colptr_like, int64_t ncol, float* F_out, int k, const double* gram,
+                  double L1, double L2, double* rowsum) {
+    if (!h || !B || !colptr_like || !F_out || !gram || !rowsum) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    if (ncol == 0) {
+        SGL_CUDA(cudaMemsetAsync(rowsum, 0, sizeof(double) * kp_of(k), h->stream));
+        return SGL_OK;
+    }
+    return dev_solve(h, B, 1, colptr_like, ncol, nullptr, nullptr, F_out, k, gram, L1, L2, rowsum);
 }
 int sgl_dev_finish_d(sgl_handle* h, int k, double* d) {
     if (!h || !d) return fail(SGL_EINVAL, "NULL argument");

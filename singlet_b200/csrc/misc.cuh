@@ -93,6 +93,16 @@ __global__ void scale_kernel(float* __restrict__ X, int64_t n_elems, int KP, con
     }
 }
 
+// out[e] = sum over splits of parts[s][e] (fixed order)
+__global__ void sum_splits_kernel(const float* __restrict__ parts, int splits, int64_t n, float* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) {
+        float s = 0.f;
+        for (int q = 0; q < splits; ++q) s += parts[(int64_t)q * n + e];
+        out[e] = s;
+    }
+}
+
 // cor (src/singlet.cpp:184-197): five running sums in FP64 -> per-CTA partials [grid][5]
 __global__ void __launch_bounds__(256)
 cor_partial_kernel(const float* __restrict__ X, const float* __restrict__ Y, int64_t n_elems,
@@ -339,30 +349,32 @@ mse_kernel(const int64_t* __restrict__ colptr, const uint2* __restrict__ rec, co
 // ----------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(256)
-synth_kernel(SynthSpec sp, int orientation, int64_t col0, int64_t ncol, int64_t* __restrict__ counts,
-             const int64_t* __restrict__ colptr, uint2* __restrict__ rec) {
+synth_kernel(SynthSpec sp, int orientation, int64_t col0, int64_t ncol, int64_t row0, int64_t nrows,
+             int64_t* __restrict__ counts, const int64_t* __restrict__ colptr, uint2* __restrict__ rec) {
     const int lane = threadIdx.x & 31;
     const int64_t lc = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (lc >= ncol) return;
     const int64_t col = col0 + lc;
-    const int64_t n_cand = orientation == 0 ? (sp.m + sp.S - 1) / sp.S : sp.n;
+    // candidates: strata (orientation 0) or cells (orientation 1) that can hit a row of [row0, row0 + nrows)
+    const int64_t c_begin = orientation == 0 ? row0 / sp.S : row0;
+    const int64_t c_end = orientation == 0 ? (row0 + nrows + sp.S - 1) / sp.S : row0 + nrows;
     const int64_t out0 = (MODE == 1) ? colptr[lc] : 0;
     int64_t n_out = 0;
-    for (int64_t c0 = 0; c0 < n_cand; c0 += 32) {
+    for (int64_t c0 = c_begin; c0 < c_end; c0 += 32) {
         const int64_t cand = c0 + lane;
         bool hit = false;
         int64_t gene = 0;
         float value = 0.f;
-        if (cand < n_cand) {
+        if (cand < c_end) {
             if (orientation == 0) {
-                hit = synth_entry(sp, (uint64_t)col, (uint32_t)cand, gene, value);
+                hit = synth_entry(sp, (uint64_t)col, (uint32_t)cand, gene, value) && gene >= row0 && gene < row0 + nrows;
             } else {
                 hit = synth_entry(sp, (uint64_t)cand, (uint32_t)(col / sp.S), gene, value) && gene == col;
             }
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, hit);
         if (MODE == 1 && hit) {
-            const uint32_t row = (uint32_t)(orientation == 0 ? gene : cand);
+            const uint32_t row = (uint32_t)((orientation == 0 ? gene : cand) - row0);
             rec[out0 + n_out + __popc(bal & ((1u << lane) - 1u))] = make_uint2(row, __float_as_uint(value));
         }
         n_out += __popc(bal);

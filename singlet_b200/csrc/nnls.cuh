@@ -91,16 +91,16 @@ __constant__ float c_inv_diag[64];
 // writes it back and claims the next unsolved column from a global counter instead of idling until the
 // slowest lane of its warp finishes. Columns are independent, so the result does not depend on which
 // lane solves which column. Row sums are taken afterwards by rowsum_partial_kernel.
-template <int KP>
-__global__ void __launch_bounds__(NnlsCfg<KP>::THREADS, NnlsCfg<KP>::MIN_CTAS)
+// NT threads per CTA, NCL columns per lane: <THREADS, 2> for large column counts; <32, 1> when there are
+// too few columns to fill the chip otherwise (e.g. a gene shard of the W update on 8 GPUs).
+template <int KP, int NT, int NCL>
+__global__ void __launch_bounds__(NT, (NT == 32) ? 8 : NnlsCfg<KP>::MIN_CTAS)
 nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
                  int splits, float* __restrict__ X,  // [ncol][KP] warm start in / solution out
                  const int64_t* __restrict__ colptr, int64_t ncol, int k, float L1, float L2,
                  unsigned long long* __restrict__ next_col,  // global work counter (zeroed by the host)
                  unsigned long long* __restrict__ stats)     // optional: [0] += sweeps, [1] += columns solved
 {
-    constexpr int NT = NnlsCfg<KP>::THREADS;
-    constexpr int NCL = 2;
     __shared__ float sx[NCL * KP * NT];  // sx[(s * KP + i) * NT + tid]
 
     const int lane = threadIdx.x & 31;

@@ -12,6 +12,14 @@ transpose" of gene blocks (R/cross_validate_nmf.R:37-50). That chunk layout maps
   (src/singlet.cpp:220) and the partial Gram H H^T (:200-206). ``cor`` runs redundantly on the
   replicated W so every rank takes the same stopping decision.
 
+Plain (unmasked) fits use the lighter layout "B" of SURVEY.md 8e instead: only the cells are sharded.
+Rank r keeps the transpose of ITS OWN cell block (local cells x all genes), computes the partial
+W-update right-hand sides from its local H shard, and the k x m partials are reduce-scattered so
+that every rank solves one gene shard; W (3.84 MB at the headline config) is then all-gathered.
+H is never gathered (128 MB per iteration saved) and the W-update SpMM keeps all m gene columns per
+rank, which fills the SMs much better than a 1/N gene shard. Masked (CV) fits stay on layout "A"
+because the per-gene Gram corrections would otherwise need a k^2 x m all-reduce.
+
 ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the plumbing; the compute calls go to
 a *backend*: :class:`CudaBackend` (the C ABI device layer) in production. The CPU tests inject their
 own oracle-backed backend to check the sharding/collective logic -- nothing in this package ever
@@ -85,6 +93,34 @@ class CudaBackend:
                                              int(ncol), table.ctypes.data, C.byref(m)))
         self._mats.append(m)
         return m
+
+    def synth_block(self, m_genes, n_cells, density, seed, orientation, col0, ncol, row0, nrows, table):
+        table = np.ascontiguousarray(table, dtype=np.float32)
+        m = C.c_void_p()
+        _lib.check(self.lib.sgl_matrix_synth_block(self._h, m_genes, n_cells, float(density), int(seed), int(orientation),
+                                                   int(col0), int(ncol), int(row0), int(nrows), table.ctypes.data, C.byref(m)))
+        self._mats.append(m)
+        return m
+
+    def column_counts(self, m):
+        """Non-zeros per column as a float64 device tensor (for the global empty-column test)."""
+        nrow, ncol, nnz = self.matrix_info(m)
+        cp = torch.zeros(ncol + 1, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.sgl_matrix_colptr(self._h, m, cp.data_ptr()))
+        return (cp[1:] - cp[:-1]).to(torch.float64)
+
+    def colptr_like(self, counts):
+        """int64[ncol + 1] with equal consecutive entries exactly where counts == 0."""
+        cp = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=counts.device)
+        cp[1:] = torch.cumsum((counts > 0).to(torch.int64), dim=0)
+        return cp
+
+    def rhs(self, X, F_in, k, B_out):
+        _lib.check(self.lib.sgl_dev_rhs(self._h, X, F_in.data_ptr(), k, B_out.data_ptr()))
+
+    def solve(self, B, colptr_like, ncol, F_out, k, gram, L1, L2, rowsum):
+        _lib.check(self.lib.sgl_dev_solve(self._h, B.data_ptr(), colptr_like.data_ptr(), int(ncol), F_out.data_ptr(), k,
+                                          gram.data_ptr(), float(L1), float(L2), rowsum.data_ptr()))
 
     def matrix_info(self, m):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
@@ -167,10 +203,15 @@ class ShardedNMF:
     (``None`` or world size 1: no collective is issued at all)."""
 
     def __init__(self, backend, m: int, n: int, k: int, A_shard, At_shard, rank: int = 0, world: int = 1, group=None,
-                 mask_A=None, mask_At=None):
+                 mask_A=None, mask_At=None, layout: str = "A"):
+        """layout "A": At_shard = this rank's genes over ALL cells. layout "B" (plain fits only): At_shard =
+        the transpose of this rank's own cell block (local cells x all genes)."""
         self.be, self.m, self.n, self.k = backend, m, n, k
         self.rank, self.world, self.group = rank, world, group
         self.A, self.At, self.mask_A, self.mask_At = A_shard, At_shard, mask_A, mask_At
+        self.layout = layout
+        if layout == "B" and (mask_A is not None or mask_At is not None):
+            raise ValueError("layout B does not support the masked (CV) solve")
         self.c0, self.c1, self.c_per = shard_bounds(n, world, rank)
         self.g0, self.g1, self.g_per = shard_bounds(m, world, rank)
         be = backend
@@ -184,6 +225,13 @@ class ShardedNMF:
         self.d = be.zeros_f64(kp)
         self.sums = be.zeros_f64(8)
         self.n_collectives = 0
+        if layout == "B":
+            # right-hand sides of all m genes (padded to g_per * world rows for the reduce-scatter) and the
+            # global "gene has any non-zero" test (src/singlet.cpp:340 skips empty columns)
+            self.Bw = be.zeros_factor(self.g_per * world, k)
+            counts = be.column_counts(self.At)
+            self._allreduce(counts)
+            self.gene_ptr = be.colptr_like(counts)
 
     # -- collectives ----------------------------------------------------------------------------
     def _allreduce(self, t):
@@ -196,6 +244,18 @@ class ShardedNMF:
         if self.world > 1:
             local = full[self.rank * per:(self.rank + 1) * per]
             dist.all_gather_into_tensor(full, local.clone(), group=self.group)
+            self.n_collectives += 1
+
+    def _reduce_scatter_rows(self, full, per):
+        """Sum `full` ([per * world][KP]) over ranks; rank r ends up with rows [r*per, (r+1)*per) summed."""
+        if self.world > 1:
+            mine = full[self.rank * per:(self.rank + 1) * per]
+            if dist.get_backend(self.group) == "gloo":  # gloo has no reduce_scatter: all-reduce, keep own rows
+                dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                out = torch.empty_like(mine)
+                dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=self.group)
+                mine.copy_(out)
             self.n_collectives += 1
 
     # -- pieces ---------------------------------------------------------------------------------
@@ -219,8 +279,42 @@ class ShardedNMF:
         be.scale(out_local, k, hi - lo, self.d)
         self._allgather_rows(F_full, per)
 
+    def iteration_b(self, L1_w, L1_h, L2_w, L2_h):
+        """Layout B iteration: H stays sharded, W-update right-hand sides are reduce-scattered."""
+        be, k = self.be, self.k
+        self.Wprev.copy_(self.W)
+        # H update over local cells against the replicated W (Gram from the full W: no collective)
+        be.gram(self.W, k, self.m, self.gram, jitter=True)
+        h_local = self.H[self.c0:self.c0 + self.c_per]
+        be.update(self.A, None, self.W, h_local, k, self.gram, L1_h, L2_h, self.d)
+        self._allreduce(self.d)
+        be.finish_d(k, self.d)
+        be.scale(h_local, k, self.c1 - self.c0, self.d)
+        # W update: partial Gram and partial right-hand sides from the local cells
+        be.gram(h_local, k, self.c1 - self.c0, self.gram, jitter=False)
+        self._allreduce(self.gram)
+        be.gram_jitter(k, self.gram)
+        be.rhs(self.At, h_local, k, self.Bw)
+        self._reduce_scatter_rows(self.Bw, self.g_per)
+        w_local = self.W[self.g0:self.g0 + self.g_per]
+        be.solve(self.Bw[self.g0:self.g0 + self.g_per], self.gene_ptr[self.g0:self.g0 + self.g_per + 1] if self.g1 > self.g0
+                 else self.gene_ptr[0:1], self.g1 - self.g0, w_local, k, self.gram, L1_w, L2_w, self.d)
+        self._allreduce(self.d)
+        be.finish_d(k, self.d)
+        be.scale(w_local, k, self.g1 - self.g0, self.d)
+        self._allgather_rows(self.W, self.g_per)
+        be.cor_sums(self.W, self.Wprev, k, self.m, self.sums)
+        s = self.sums[:5].cpu().numpy()
+        return be.cor_from_sums(s, float(k) * float(self.m))
+
+    def gather_h(self):
+        """Layout B keeps H sharded; gather it once (e.g. for the final output)."""
+        self._allgather_rows(self.H, self.c_per)
+
     def iteration(self, L1_w, L1_h, L2_w, L2_h):
         """One trip of src/singlet.cpp:648-659. Returns tol (1 - cor) as a python float (synchronises)."""
+        if self.layout == "B":
+            return self.iteration_b(L1_w, L1_h, L2_w, L2_h)
         be, k = self.be, self.k
         self.Wprev.copy_(self.W)
         # H update over local cells; Gram of W: each rank sums its own genes
@@ -241,6 +335,8 @@ class ShardedNMF:
         return float(out.cpu().numpy()[0]) / float(self.n)
 
     def factors_to_host(self):
+        if self.layout == "B":
+            self.gather_h()
         w = self.be.factor_to_host(self.W, self.k, self.m)
         h = self.be.factor_to_host(self.H, self.k, self.n)
         d = self.d[: self.k].cpu().numpy().copy()
@@ -248,9 +344,10 @@ class ShardedNMF:
 
 
 def sharded_nmf(backend, m, n, k, A_shard, At_shard, w_init, tol=1e-4, maxit=100, L1=(0.01, 0.01), L2=(0.0, 0.0), rank=0,
-                world=1, group=None):
-    """``c_nmf`` over shards (reference src/singlet.cpp:638-666). Returns dict(w, d, h, iter, tol)."""
-    fit = ShardedNMF(backend, m, n, k, A_shard, At_shard, rank, world, group)
+                world=1, group=None, layout="A"):
+    """``c_nmf`` over shards (reference src/singlet.cpp:638-666). Returns dict(w, d, h, iter, tol).
+    layout "A": At_shard = gene block over all cells; "B": At_shard = transpose of the local cell block."""
+    fit = ShardedNMF(backend, m, n, k, A_shard, At_shard, rank, world, group, layout=layout)
     fit.set_w(w_init)
     tol_, it = 1.0, 0
     while it < maxit and tol_ > tol:

@@ -23,6 +23,8 @@ def test_sharded_driver_world1_matches_c_driver(oracle):
         s = sharded_nmf(be, m, n, k, hA, hAt, w0, tol=0.0, maxit=6, L1=(0.01, 0.01))
         c = api.c_nmf(A, At, 0.0, 6, False, 0.01, 0.01, 0, 0, 0, w0)
         assert np.array_equal(s["w"], c["w"]) and np.array_equal(s["h"], c["h"]) and np.allclose(s["d"], c["d"], rtol=1e-12)
+        sb = sharded_nmf(be, m, n, k, hA, hAt, w0, tol=0.0, maxit=6, L1=(0.01, 0.01), layout="B")  # world 1: At is the full transpose
+        assert np.array_equal(sb["w"], c["w"]) and np.array_equal(sb["h"], c["h"])
         sm = sharded_ard_nmf(be, m, n, k, hA, hAt, w0, 123, 20, tol=0.0, maxit=5, overfit_threshold=10.0, trace_test_mse=2)
         cm = api.c_ard_nmf(A, At, 0.0, 5, False, 0.01, 0, 0, w0, 123, 20, 10.0, 2)
         assert np.array_equal(sm["iter"], cm["iter"]) and np.allclose(sm["test_mse"], cm["test_mse"], rtol=1e-12)
@@ -62,6 +64,31 @@ def test_two_virtual_shards_on_one_gpu(oracle):
             tot += rs.cpu().numpy()
         assert np.array_equal(Hparts.cpu().numpy(), Hfull.cpu().numpy())
         assert np.allclose(tot, rs_full.cpu().numpy(), rtol=1e-12)
+        # layout B pieces: partial right-hand sides of the two cell blocks add up to the full ones, and the
+        # device block generator equals the corresponding slice of the transpose
+        from singlet_b200 import _lib as L
+        At_full = be.upload(At)
+        Bfull, Bpart, Bsum = be.zeros_factor(m, k), be.zeros_factor(m, k), be.zeros_factor(m, k)
+        be.rhs(At_full, Hfull, k, Bfull)
+        for r in range(2):
+            lo, hi, per = shard_bounds(n, 2, r)
+            blk = be.upload(A[:, lo:hi].T.tocsc())
+            be.rhs(blk, Hfull[lo:hi], k, Bpart)
+            Bsum += Bpart
+        assert np.allclose(Bsum.cpu().numpy(), Bfull.cpu().numpy(), rtol=2e-5, atol=1e-6)
+        tab = synth.values_table(m, 0.06)
+        S = synth.synth_scipy(m, n, 0.06, seed=18)
+        lo, hi, per = shard_bounds(n, 2, 1)
+        dev_blk = be.synth_block(m, n, 0.06, 18, 1, 0, m, lo, hi - lo, tab)
+        p, i, x, nrow, ncol = be.matrix_to_host(dev_blk)
+        T = S[:, lo:hi].T.tocsc()
+        T.sort_indices()
+        assert (nrow, ncol) == T.shape and np.array_equal(p, T.indptr) and np.array_equal(i, T.indices) and np.array_equal(x, T.data)
+        dev_blk0 = be.synth_block(m, n, 0.06, 18, 0, 5, 40, 100, 300, tab)
+        p, i, x, nrow, ncol = be.matrix_to_host(dev_blk0)
+        T0 = S[100:400, 5:45].tocsc()
+        T0.sort_indices()
+        assert np.array_equal(p, T0.indptr) and np.array_equal(i, T0.indices) and np.array_equal(x, T0.data)
         # masked shards hash with global column offsets
         mfull = be.mask_build(full, 123, 20, 0, 0, 0)
         lo, hi, per = shard_bounds(n, 2, 1)

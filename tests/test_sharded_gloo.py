@@ -88,6 +88,29 @@ class OracleBackend:
         rs[:k] = F_out[: X.shape[1], :k].sum(dim=0)
         rowsum.copy_(rs)
 
+    def column_counts(self, X):
+        return torch.from_numpy(np.diff(X.indptr).astype(np.float64))
+
+    def colptr_like(self, counts):
+        cp = torch.zeros(counts.numel() + 1, dtype=torch.int64)
+        cp[1:] = torch.cumsum((counts > 0).to(torch.int64), dim=0)
+        return cp
+
+    def rhs(self, X, F_in, k, B_out):
+        B_out[: X.shape[1], :k] = torch.from_numpy((X.T @ F_in[: X.shape[0], :k].numpy()))
+
+    def solve(self, B, colptr_like, ncol, F_out, k, gram, L1, L2, rowsum):
+        kp = self.kp(k)
+        a = gram.view(kp, kp)[:k, :k].numpy().copy()
+        for c in range(ncol):
+            if colptr_like[c] == colptr_like[c + 1]:
+                continue
+            x, _, _ = self.orc.nnls(a, B[c, :k].numpy(), F_out[c, :k].numpy(), L1, L2)
+            F_out[c, :k] = torch.from_numpy(x)
+        rs = torch.zeros(kp, dtype=torch.float64)
+        rs[:k] = F_out[:ncol, :k].sum(dim=0)
+        rowsum.copy_(rs)
+
     def finish_d(self, k, d):
         d[:k] += 1e-15
         d[k:] = 1.0
@@ -134,7 +157,10 @@ def _worker(rank, world, port, q):
                           rank=rank, world=world)
         cv = sharded_ard_nmf(be, m, n, k, A[:, c0:c1].tocsc(), At[:, g0:g1].tocsc(), w0, 123, 5, tol=0.0, maxit=3,
                              overfit_threshold=10.0, trace_test_mse=2, rank=rank, world=world)
-        q.put((rank, res["w"], res["h"], res["d"], res["tol"], cv["test_mse"], cv["h"]))
+        # layout B: the rank's transpose block covers its own cells only
+        resb = sharded_nmf(be, m, n, k, A[:, c0:c1].tocsc(), A[:, c0:c1].T.tocsc(), w0, tol=0.0, maxit=4, L1=(0.01, 0.02),
+                           rank=rank, world=world, layout="B")
+        q.put((rank, res["w"], res["h"], res["d"], res["tol"], cv["test_mse"], cv["h"], resb["w"], resb["h"], resb["d"]))
     finally:
         dist.destroy_process_group()
 
@@ -158,10 +184,12 @@ def test_two_rank_gloo_matches_unsharded_oracle(oracle):
     w0 = synth.w_init(k, m, seed=2)
     ref = oracle.nmf(A, At, w0, tol=0.0, maxit=4, L1=(0.01, 0.02))
     cvr = oracle.ard_nmf(A, At, w0, 123, 5, tol=0.0, maxit=3, overfit_threshold=10.0, trace_test_mse=2)
-    for rank, w, h, d, tol, mse, hcv in outs:  # every rank ends with the full replicated model
+    for rank, w, h, d, tol, mse, hcv, wb, hb, db in outs:  # every rank ends with the full replicated model
         assert np.allclose(w, ref["w"], rtol=1e-9, atol=1e-12) and np.allclose(h, ref["h"], rtol=1e-9, atol=1e-12)
         assert np.allclose(d, ref["d"], rtol=1e-9) and abs(tol - ref["tol"][-1]) < 1e-9
         assert np.allclose(mse, cvr["test_mse"], rtol=1e-9) and np.allclose(hcv, cvr["h"], rtol=1e-8, atol=1e-12)
+        assert np.allclose(wb, ref["w"], rtol=1e-9, atol=1e-12) and np.allclose(hb, ref["h"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(db, ref["d"], rtol=1e-9)
 
 
 def test_shard_bounds_cover_everything():
