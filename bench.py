@@ -109,6 +109,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(config_name, world):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if not captured for
+    this configuration)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+            t = json.load(fh)
+        if t.get("config") == config_name and t.get("n_gpus") == world:
+            mean_read = 0.5 * (t["dram_bytes_read_per_launch"] + t["w_update_launch"]["dram_bytes_read"])
+            mean_write = 0.5 * (t["dram_bytes_write_per_launch"] + t["w_update_launch"]["dram_bytes_write"])
+            return mean_read + mean_write
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -130,7 +145,8 @@ def cpu_reference_leg(cfg, steps, warmup, sample_cells, backend=None):
 
     kind = "reference" if have_reference() else "port"
     orc = Oracle(kind)
-    cores = orc.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every host core explicitly
+    cores = max(orc.max_threads(), os.cpu_count() or 1)
     m, n, dens, k = cfg["m"], cfg["n"], cfg["density"], cfg["k"]
     if sample_cells <= 0:
         # ~1.5e6 non-zeros per core and per iteration keeps one iteration in the seconds range
@@ -147,7 +163,7 @@ def cpu_reference_leg(cfg, steps, warmup, sample_cells, backend=None):
     times = []
     for rep in range(max(1, min(warmup, 1)) + max(1, min(steps, 3))):
         t0 = time.perf_counter()
-        orc.nmf(A, At, w0, tol=0.0, maxit=1, L1=(L1, L1), L2=(L2, L2))
+        orc.nmf(A, At, w0, tol=0.0, maxit=1, L1=(L1, L1), L2=(L2, L2), threads=cores)
         times.append(time.perf_counter() - t0)
     per_iter = float(np.median(times[1:])) if len(times) > 1 else times[0]
     its_sample = 1.0 / per_iter
@@ -280,7 +296,8 @@ def main():
                "config": dict(base_cfg, nnz=nnz_total, generate_s=round(t_gen, 3), final_tol=tol),
                "gpu_launches": total_launches, "clocks": clocks,
                "roofline": {"bound": "hbm", "kernel": "spmm_stream_kernel<32> (mean of the H-update and W-update launches, rank 0)",
-                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": ncu_traffic(args.config, world),
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes,
                             "ms_per_launch": per_launch_ms, "launches_timed": spmm_cnt},
                "breakdown_ms_per_step_rank0": {"spmm": spmm_ms / args.steps, "nnls": prof["nnls"][0] / args.steps,
@@ -290,15 +307,17 @@ def main():
 
     # ---- e2e: host buffers through the C ABI (rank 0 drives all N GPUs' worth of data only at N = 1) ----
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         try:
-            e2e = e2e_leg(be, cfg, args.steps, A_sh, At_sh)
+            if world == 1:
+                e2e = e2e_leg(be, cfg, args.steps, A_sh, At_sh)
+            else:
+                e2e = e2e_leg_sharded(be, cfg, args.steps, A_sh, At_sh, rank, world, group)
         except MemoryError as ex:
             e2e = {"value": None, "unit": "iterations/s", "error": f"host memory: {ex}"}
     if rank == 0:
         out["e2e"] = e2e if e2e is not None else {"value": None, "unit": "iterations/s", "h2d_bytes_per_step": None,
-                                                  "d2h_bytes_per_step": None,
-                                                  "note": "host-buffer leg runs at N=1 only (sgl_nmf drives one GPU)"}
+                                                  "d2h_bytes_per_step": None, "note": "skipped (--no-e2e)"}
         if not args.no_cpu:
             be_cpu = be
             out["cpu_baseline"] = cpu_reference_leg(cfg, args.steps, args.warmup, args.cpu_sample_cells, be_cpu)
@@ -307,6 +326,46 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def e2e_leg_sharded(be, cfg, steps, A_dev, At_dev, rank, world, group):
+    """N > 1: every rank starts from HOST dgCMatrix shards (its cells, and the transpose of that block), uploads
+    them, runs `steps` iterations of the sharded fit and downloads the replicated model. Max over ranks."""
+    import scipy.sparse as sp
+    import torch
+    import torch.distributed as dist
+
+    from singlet_b200 import synth
+    from singlet_b200.sharded import ShardedNMF, shard_bounds
+
+    m, n, k = cfg["m"], cfg["n"], cfg["k"]
+    c0, c1, _ = shard_bounds(n, world, rank)
+    pA, pAt = be.matrix_to_host(A_dev), be.matrix_to_host(At_dev)
+    A = sp.csc_matrix((pA[2], pA[1], pA[0]), shape=(m, c1 - c0))
+    At = sp.csc_matrix((pAt[2], pAt[1], pAt[0]), shape=(c1 - c0, m))
+    A.has_sorted_indices = At.has_sorted_indices = True
+    w0 = synth.w_init(k, m)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    hA, hAt = be.upload(A), be.upload(At)
+    fit = ShardedNMF(be, m, n, k, hA, hAt, rank, world, group, layout="B")
+    fit.set_w(w0)
+    for _ in range(steps):
+        fit.iteration(L1, L1, L2, L2)
+    w, d, h = fit.factors_to_host()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=be.device)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    h2d = torch.tensor([float(A.data.nbytes + A.indices.nbytes + A.indptr.nbytes + At.data.nbytes + At.indices.nbytes
+                              + At.indptr.nbytes + w0.nbytes)], dtype=torch.float64, device=be.device)
+    dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+    d2h = float(world) * (w.nbytes + h.nbytes + d.nbytes + steps * 40)
+    sec = float(dt[0])
+    return {"value": steps / sec, "unit": "iterations/s", "h2d_bytes_per_step": float(h2d[0]) / steps, "d2h_bytes_per_step": d2h / steps,
+            "seconds_total": sec, "iterations": steps,
+            "note": "sharded public API (singlet_b200.sharded): every rank uploads its host dgCMatrix shards (FP64), K "
+                    "iterations, replicated w/d/h downloaded on every rank; max over ranks"}
 
 
 def e2e_leg(be, cfg, steps, A_dev, At_dev):
