@@ -39,6 +39,8 @@ sys.path.insert(0, ROOT)
 CONFIGS = {
     # BASELINE.json configs[2]: the configuration the metric is quoted on
     "c3": dict(m=30000, n=1000000, density=0.05, k=32, name="synthetic 30k genes x 1M cells, 5% density, run_nmf k=32"),
+    # BASELINE.json configs[4]: atlas scale, needs several GPUs (4.2e9 non-zeros: beyond one dgCMatrix's int32 pointers)
+    "c5": dict(m=35000, n=4000000, density=0.03, k=64, name="synthetic 35k genes x 4M cells, 3% density, k=64 (atlas scale)"),
     # smaller stand-ins for quick checks (never the default)
     "mid": dict(m=30000, n=100000, density=0.05, k=32, name="MID 30k x 100k (not a bench config)"),
     "mini": dict(m=3000, n=20000, density=0.05, k=32, name="MINI 3k x 20k (not a bench config)"),
