@@ -95,6 +95,14 @@ int sgl_nmf(sgl_handle* h, const sgl_csc* A, int nA, const sgl_csc* At, int nAt,
             double L1_w, double L1_h, double L2_w, double L2_h, int k, double* w, double* d, double* h_out,
             int32_t* iters_out, double* tol_out, const sgl_callbacks* cb);
 
+/* c_linked_nmf: src/singlet.cpp:1059-1086 with predict_link :416-433 (RcppExports.R:74-76). link_h is
+ * lh_rows x lh_cols, link_w is lw_rows x lw_cols (column-major doubles); like the reference a side is linked only
+ * when its matrix has one column per cell (link_h) / per gene (link_w), otherwise that half-iteration is plain. */
+int sgl_linked_nmf(sgl_handle* h, const sgl_csc* A, const sgl_csc* At, double tol, uint16_t maxit, double L1, double L2,
+                   int k, double* w, double* d, double* h_out, const double* link_h, int lh_rows, int64_t lh_cols,
+                   const double* link_w, int lw_rows, int64_t lw_cols, int32_t* iters_out, double* tol_out,
+                   const sgl_callbacks* cb);
+
 /* c_ard_nmf / c_ard_nmf_sparse_list: src/singlet.cpp:1090-1234 (RcppExports.cpp:283-327). */
 int sgl_ard_nmf(sgl_handle* h, const sgl_csc* A, int nA, const sgl_csc* At, int nAt, double tol, uint16_t maxit,
                 double L1, double L2, int k, double* w, double* d, double* h_out, uint64_t seed,

@@ -95,9 +95,11 @@ class Oracle:
         f("ard_nmf", i32, [vp, i32, vp, i32, dbl, C.c_uint16, dbl, dbl, i32, i32, vp, vp, vp, u64, u64, dbl,
                            C.c_uint16, vp, vp, vp, vp, i32, vp])
         f("project_model", None, [vp, i32, vp, i32, dbl, dbl, i32, vp, vp])
+        f("linked_nmf", i32, [vp, vp, dbl, C.c_uint16, dbl, dbl, i32, i32, vp, vp, vp, vp, i32, i64, vp, i32, i64])
         f("max_threads", i32, [])
         if kind == "port":
             f("mse_train", dbl, [vp, i32, vp, vp, vp, i32, u64, u64, i32])
+            f("weight_by_split", None, [vp, vp, vp, i32])
             f("mask_cell", None, [u64, u64, u64, u64, vp])
 
     def _f(self, name, res, args):
@@ -220,6 +222,30 @@ class Oracle:
         q = nt.value
         return {"w": w, "d": d, "h": h, "test_mse": mse[:q].copy(), "iter": it[:q].copy(), "tol": ft[:q].copy(),
                 "score_overfit": so[:q].copy(), "last_iter": last}
+
+    def linked_nmf(self, A, At, w_init, link_h, link_w, tol=1e-4, maxit=100, L1=0.01, L2=0.0, threads=0):
+        """c_linked_nmf: link_h / link_w are (rows x cols) matrices; a side is linked only when its matrix has one
+        column per cell (link_h) / per gene (link_w), like the reference."""
+        a, na, k1 = _as_chunks(A)
+        at, nat, k2 = _as_chunks(At)
+        w = np.array(w_init, np.float64, order="F")
+        k, m = w.shape
+        n = int(a[0].ncol)
+        lh = np.asfortranarray(link_h, np.float64)
+        lw = np.asfortranarray(link_w, np.float64)
+        d = np.zeros(k, np.float64)
+        h = np.zeros((k, n), np.float64, order="F")
+        self._linked_nmf(a, at, tol, maxit, L1, L2, threads, k, _dp(w), _dp(d), _dp(h), _dp(lh), lh.shape[0], lh.shape[1],
+                         _dp(lw), lw.shape[0], lw.shape[1])
+        return {"w": w, "d": d, "h": h}
+
+    def weight_by_split(self, A, split_by, n_groups):
+        """Returns the re-weighted values (port only)."""
+        a, na, keep = _as_chunks(A)
+        x = np.array(A.data if hasattr(A, "data") else A[2], np.float64)
+        sb = np.ascontiguousarray(split_by, np.int32)
+        self._weight_by_split(a, _dp(x), _dp(sb), int(n_groups))
+        return x
 
     def project_model(self, A, w, L1=0.01, L2=0.0, threads=0):
         a, na, keep = _as_chunks(A)

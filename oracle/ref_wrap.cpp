@@ -180,6 +180,18 @@ void ref_project_model(const orc_csc* A, int, double* w, int k, double L1, doubl
     put(out, "d", d);
 }
 
+int ref_linked_nmf(const orc_csc* A, const orc_csc* At, double tol, uint16_t maxit, double L1, double L2, int threads, int k,
+                   double* w, double* d, double* h, const double* link_h, int lh_rows, int64_t lh_cols, const double* link_w,
+                   int lw_rows, int64_t lw_cols) {
+    Eigen::MatrixXd wm = mat(w, k, (long)A[0].nrow);
+    Eigen::MatrixXd lh = mat(link_h, lh_rows, (long)lh_cols), lw = mat(link_w, lw_rows, (long)lw_cols);
+    Rcpp::List out = c_linked_nmf(view(A[0]), view(At[0]), tol, maxit, false, L1, L2, (uint16_t)threads_or_all(threads), wm, lh, lw);
+    put(out, "w", w);
+    put(out, "d", d);
+    put(out, "h", h);
+    return -1;
+}
+
 int ref_max_threads(void) { return threads_or_all(0); }
 
 }  // extern "C"

@@ -195,6 +195,33 @@ void orc_predict(const orc_csc* A, int n_chunks, const double* w, int k, double*
     if (sweeps_out) *sweeps_out = sweeps;
 }
 
+// predict_link: as predict, with b multiplied element-wise by column c of `link` (link_rows x n_total,
+// column-major) before the solve. Reference src/singlet.cpp:416-433.
+void orc_predict_link(const orc_csc* A, int n_chunks, const double* w, int k, double* h, double L1, double L2,
+                      int threads, const double* link, int link_rows) {
+    const int64_t rows = A[0].nrow;
+    std::vector<double> a((size_t)k * k);
+    orc_gram(w, k, rows, a.data());
+    int64_t offset = 0;
+    const int nt = resolve_threads(threads);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const orc_csc& M = A[ch];
+#pragma omp parallel for num_threads(nt)
+        for (int64_t c = 0; c < M.ncol; ++c) {
+            if (M.p[c] == M.p[c + 1]) continue;
+            std::vector<double> b((size_t)k, 0.0);
+            for (int32_t t = M.p[c]; t < M.p[c + 1]; ++t) {
+                const double v = M.x[t];
+                const double* wr = w + (size_t)M.i[t] * k;
+                for (int f = 0; f < k; ++f) b[f] += v * wr[f];
+            }
+            for (int j = 0; j < link_rows; ++j) b[j] *= link[(size_t)(c + offset) * link_rows + j];
+            orc_nnls(a.data(), b.data(), h + (size_t)(c + offset) * k, k, L1, L2);
+        }
+        offset += M.ncol;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // predict_mask: as predict, with the speckled test set held out.
 // Reference src/singlet.cpp:436-466 (single) and :469-503 (list). mask_t == 0: columns are
@@ -374,6 +401,43 @@ int orc_nmf(const orc_csc* A, int nA, const orc_csc* At, int nAt, double tol, ui
         if (tol_trace) tol_trace[iter_] = tol_;
     }
     return (int)iter_;
+}
+
+// Linked NMF. Reference src/singlet.cpp:1059-1086: linking is applied to the H update when link_h has one
+// column per cell, to the W update when link_w has one column per gene; otherwise that side is plain.
+int orc_linked_nmf(const orc_csc* A, const orc_csc* At, double tol, uint16_t maxit, double L1, double L2, int threads, int k,
+                   double* w, double* d, double* h, const double* link_h, int lh_rows, int64_t lh_cols, const double* link_w,
+                   int lw_rows, int64_t lw_cols) {
+    const int64_t m = A[0].nrow, n = A[0].ncol;
+    std::memset(h, 0, sizeof(double) * (size_t)k * (size_t)n);
+    for (int f = 0; f < k; ++f) d[f] = 1.0;
+    const bool linking_h = (lh_cols == n), linking_w = (lw_cols == m);
+    double tol_ = 1;
+    std::vector<double> w_it((size_t)k * (size_t)m);
+    uint16_t iter_ = 0;
+    for (; iter_ < maxit && tol_ > tol; ++iter_) {
+        std::memcpy(w_it.data(), w, sizeof(double) * w_it.size());
+        if (linking_h) orc_predict_link(A, 1, w, k, h, L1, L2, threads, link_h, lh_rows);
+        else orc_predict(A, 1, w, k, h, L1, L2, threads, nullptr);
+        orc_scale(h, k, n, d);
+        if (linking_w) orc_predict_link(At, 1, h, k, w, L1, L2, threads, link_w, lw_rows);
+        else orc_predict(At, 1, h, k, w, L1, L2, threads, nullptr);
+        orc_scale(w, k, m, d);
+        tol_ = orc_cor(w, w_it.data(), (uint64_t)k * (uint64_t)m);
+    }
+    return (int)iter_;
+}
+
+// weight_by_split. Reference src/singlet.cpp:119-144: every group's total is made equal to group 0's by
+// dividing the values of the columns of group g != 0 by sums[g] / sums[0]. x is modified in place.
+void orc_weight_by_split(const orc_csc* A, double* x, const int32_t* split_by, int n_groups) {
+    std::vector<double> sums((size_t)n_groups, 0.0);
+    for (int64_t j = 0; j < A->ncol; ++j)
+        for (int32_t t = A->p[j]; t < A->p[j + 1]; ++t) sums[(size_t)split_by[j]] += x[t];
+    for (int g = 1; g < n_groups; ++g) sums[(size_t)g] /= sums[0];
+    for (int64_t j = 0; j < A->ncol; ++j)
+        if (split_by[j] != 0)
+            for (int32_t t = A->p[j]; t < A->p[j + 1]; ++t) x[t] /= sums[(size_t)split_by[j]];
 }
 
 // Cross-validated ("ard") ALS NMF with speckled mask. Reference src/singlet.cpp:1091-1152 and

@@ -125,6 +125,23 @@ Rcpp::List c_nmf_sparse_list(Rcpp::List A_, Rcpp::List& At_, const double tol, c
     return nmf_impl(views(A), views(At), tol, maxit, verbose, L1, L1, L2, L2, w);
 }
 
+// "next" row f2: linked NMF (reference src/singlet.cpp:1059-1086, called by R/RunLNMF.R:60)
+//[[Rcpp::export]]
+Rcpp::List c_linked_nmf(Rcpp::SparseMatrix A, Rcpp::SparseMatrix At, const double tol, const uint16_t maxit, const bool verbose,
+                        const double L1, const double L2, const uint16_t threads, Eigen::MatrixXd w, Eigen::MatrixXd link_h,
+                        Eigen::MatrixXd link_w) {
+    const int k = (int)w.rows();
+    Eigen::MatrixXd h(k, (int64_t)A.cols());
+    Eigen::VectorXd d(k);
+    Progress p{verbose, false};
+    sgl_callbacks cb = callbacks(p);
+    if (verbose) Rprintf("\n%4s | %8s \n---------------\n", "iter", "tol");
+    sgl_csc a = view(A), at = view(At);
+    check(sgl_linked_nmf(handle(), &a, &at, tol, maxit, L1, L2, k, w.data(), d.data(), h.data(), link_h.data(), (int)link_h.rows(),
+                         link_h.cols(), link_w.data(), (int)link_w.rows(), link_w.cols(), nullptr, nullptr, &cb));
+    return Rcpp::List::create(Rcpp::Named("w") = w, Rcpp::Named("d") = d, Rcpp::Named("h") = h);
+}
+
 //[[Rcpp::export]]
 Rcpp::List c_ard_nmf(Rcpp::SparseMatrix& A, Rcpp::SparseMatrix& At, const double tol, const uint16_t maxit, const bool verbose,
                      const double L1, const double L2, const uint16_t threads, Eigen::MatrixXd w, const uint64_t seed,

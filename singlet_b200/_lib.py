@@ -58,6 +58,8 @@ SYMBOLS = [
     ("sgl_profile", _i32, [_vp, _i32]),
     ("sgl_profile_read", _i32, [_vp, _vp, _vp, _vp]),
     ("sgl_nmf", _i32, [_vp, _vp, _i32, _vp, _i32, _dbl, _u16, _dbl, _dbl, _dbl, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("sgl_linked_nmf", _i32, [_vp, _vp, _vp, _dbl, _u16, _dbl, _dbl, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i64, _vp,
+                              _vp, _vp]),
     ("sgl_ard_nmf", _i32, [_vp, _vp, _i32, _vp, _i32, _dbl, _u16, _dbl, _dbl, _i32, _vp, _vp, _vp, _u64, _u64, _dbl, _u16,
                            _vp, _vp]),
     ("sgl_project_model", _i32, [_vp, _vp, _i32, _vp, _i64, _i64, _dbl, _dbl, _vp, _vp]),

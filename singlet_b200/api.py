@@ -172,6 +172,43 @@ def c_nmf_sparse_list(A_, At_, tol, maxit, verbose, L1, L2, threads, w, handle: 
     return c_nmf(list(A_), list(At_), tol, maxit, verbose, L1, L1, L2, L2, threads, w, handle)
 
 
+def c_linked_nmf(A, At, tol, maxit, verbose, L1, L2, threads, w, link_h, link_w, handle: Handle | None = None):
+    """``c_linked_nmf`` (reference src/singlet.cpp:1059-1086; R/RcppExports.R:74-76): ALS NMF where ``b`` is
+    multiplied by a column of ``link_h`` / ``link_w`` before every solve (``predict_link`` :416-433). A side is
+    linked only when its matrix has one column per cell / per gene, like the reference."""
+    h = handle or default_handle()
+    A, At = _as_csc(A), _as_csc(At)
+    a, na, k1 = _lib.chunks_to_c(A)
+    at, nat, k2 = _lib.chunks_to_c(At)
+    wk = np.array(w, dtype=np.float64, order="F")
+    k, m = wk.shape
+    n = _ncols(A)
+    lh = np.asfortranarray(link_h, dtype=np.float64)
+    lw = np.asfortranarray(link_w, dtype=np.float64)
+    d = np.zeros(k)
+    hh = np.zeros((k, n), order="F")
+    iters, ftol = C.c_int32(0), C.c_double(0)
+    cb, keep = _callbacks(bool(verbose), False)
+    _lib.check(h.lib.sgl_linked_nmf(h.ptr, a, at, float(tol), int(maxit) & 0xFFFF, float(L1), float(L2), k, _dp(wk), _dp(d), _dp(hh),
+                                    _dp(lh), lh.shape[0], lh.shape[1], _dp(lw), lw.shape[0], lw.shape[1], C.addressof(iters),
+                                    C.addressof(ftol), C.addressof(cb) if cb is not None else None))
+    return {"w": wk, "d": d, "h": hh, "iter": iters.value, "tol": ftol.value}
+
+
+def weight_by_split(A, split_by, n_groups):
+    """``weight_by_split`` (reference src/singlet.cpp:119-144): returns a copy of the CSC matrix in which the
+    columns of every group g != 0 are divided by ``sum(group g) / sum(group 0)`` so that all groups carry the same
+    total weight (pre-processing of ``RunNMF(split.by = ...)``, R/RunNMF.R:86-97). Pure host O(nnz) work."""
+    A = _as_csc(A).copy()
+    split_by = np.asarray(split_by, dtype=np.int64)
+    per_nz = np.repeat(split_by, np.diff(A.indptr))
+    sums = np.bincount(per_nz, weights=A.data, minlength=n_groups).astype(np.float64)
+    factor = np.ones(n_groups)
+    factor[1:] = sums[1:] / sums[0]
+    A.data = np.where(per_nz != 0, A.data / factor[per_nz], A.data)
+    return A
+
+
 def c_ard_nmf(A, At, tol, maxit, verbose, L1, L2, threads, w, seed, inv_density, overfit_threshold, trace_test_mse,
               handle: Handle | None = None):
     """``c_ard_nmf`` (reference src/singlet.cpp:1155-1159; R/RcppExports.R:70-72). Returns

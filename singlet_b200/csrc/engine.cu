@@ -95,7 +95,7 @@ struct sgl_handle {
     int sm_count = 148;
     int64_t launches = 0;
     bool cache = true;
-    DevBuf<float> bparts, gram_f, gram_f_nojit, inv_diag;
+    DevBuf<float> bparts, blink, gram_f, gram_f_nojit, inv_diag;
     DevBuf<double> part, scal, losses, gram_w;
     DevBuf<int64_t> counts;
     DevBuf<unsigned long long> workctr;
@@ -596,13 +596,20 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
 
 // predict / predict_mask for all columns of X (src/singlet.cpp:333-347, 436-466)
 static int dev_update(sgl_handle* h, const sgl_matrix* X, const sgl_mask* mask, const float* F_in, float* F_out, int k,
-                      const double* gram, double L1, double L2, double* rowsum) {
+                      const double* gram, double L1, double L2, double* rowsum, const float* link = nullptr) {
     if (X->ncol == 0) {
         SGL_CUDA(cudaMemsetAsync(rowsum, 0, sizeof(double) * kp_of(k), h->stream));
         return SGL_OK;
     }
     int splits = 1;
     SGL_TRY(dev_rhs(h, X, mask, F_in, k, &splits));
+    if (link) {  // predict_link (src/singlet.cpp:416-433): b *= link[:, c] before the solve
+        const int64_t n = X->ncol * kp_of(k);
+        SGL_TRY(h->blink.ensure((size_t)n));
+        link_rhs_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->bparts.p, splits, n, link, h->blink.p);
+        LAUNCH_CHECK(h);
+        return dev_solve(h, h->blink.p, 1, X->colptr, X->ncol, mask, F_in, F_out, k, gram, L1, L2, rowsum);
+    }
     return dev_solve(h, h->bparts.p, splits, X->colptr, X->ncol, mask, F_in, F_out, k, gram, L1, L2, rowsum);
 }
 
@@ -825,17 +832,18 @@ static int check_shapes(const sgl_matrix* A, const sgl_matrix* At) {
 
 // one ALS iteration: H update, scale, W update, scale, cor  (src/singlet.cpp:648-659 / 1108-1114)
 static int als_iteration(sgl_handle* h, FitBuffers& fb, sgl_matrix* A, sgl_matrix* At, const sgl_mask* mA, const sgl_mask* mAt, int k,
-                         double L1_w, double L1_h, double L2_w, double L2_h, const sgl_callbacks* cb, double* tol_out) {
+                         double L1_w, double L1_h, double L2_w, double L2_h, const sgl_callbacks* cb, double* tol_out,
+                         const float* link_h = nullptr, const float* link_w = nullptr) {
     const int KPV = kp_of(k);
     const int64_t m = A->nrow, n = A->ncol;
     SGL_CUDA(cudaMemcpyAsync(fb.Wprev, fb.W, sizeof(float) * (size_t)m * KPV, cudaMemcpyDeviceToDevice, h->stream));
     SGL_TRY(dev_gram(h, fb.W, k, m, fb.gram, true));
-    SGL_TRY(dev_update(h, A, mA, fb.W, fb.H, k, fb.gram, L1_h, L2_h, fb.dvec));
+    SGL_TRY(dev_update(h, A, mA, fb.W, fb.H, k, fb.gram, L1_h, L2_h, fb.dvec, link_h));
     SGL_TRY(dev_finish_d(h, k, fb.dvec));
     SGL_TRY(dev_scale(h, fb.H, k, n, fb.dvec));
     if (cb && cb->poll_interrupt && cb->poll_interrupt(cb->user)) return fail(SGL_EINTERRUPT, "interrupted");
     SGL_TRY(dev_gram(h, fb.H, k, n, fb.gram, true));
-    SGL_TRY(dev_update(h, At, mAt, fb.H, fb.W, k, fb.gram, L1_w, L2_w, fb.dvec));
+    SGL_TRY(dev_update(h, At, mAt, fb.H, fb.W, k, fb.gram, L1_w, L2_w, fb.dvec, link_w));
     SGL_TRY(dev_finish_d(h, k, fb.dvec));
     SGL_TRY(dev_scale(h, fb.W, k, m, fb.dvec));
     SGL_TRY(dev_cor_sums(h, fb.W, fb.Wprev, k, m, fb.sums));
@@ -921,7 +929,7 @@ int sgl_destroy(sgl_handle* h) {
     mask_release(h->cmAt);
     matrix_release(h->cA);
     matrix_release(h->cAt);
-    h->bparts.release(); h->gram_f.release(); h->gram_f_nojit.release(); h->inv_diag.release();
+    h->bparts.release(); h->blink.release(); h->gram_f.release(); h->gram_f_nojit.release(); h->inv_diag.release();
     h->part.release(); h->scal.release(); h->losses.release(); h->gram_w.release(); h->counts.release(); h->workctr.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -993,6 +1001,57 @@ int sgl_nmf(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, int nA
     if (iters_out) *iters_out = iter_;
     if (tol_out) *tol_out = tol_;
     return fit_outputs(h, fb, k, A->nrow, A->ncol, w, d, h_out);
+}
+
+// ---- c_linked_nmf ("next" row f2) ---------------------------------------------------------
+static int link_upload(sgl_handle* h, const double* link, int rows, int64_t cols, int k, float** out) {
+    const int KPV = kp_of(k);
+    if (rows > k) return fail(SGL_EINVAL, "link matrix has %d rows but the rank is %d", rows, k);
+    double* tmp = nullptr;
+    SGL_CUDA(cudaMalloc(out, sizeof(float) * (size_t)cols * KPV));
+    SGL_CUDA(cudaMalloc(&tmp, sizeof(double) * (size_t)rows * (size_t)cols));
+    cudaMemcpyAsync(tmp, link, sizeof(double) * (size_t)rows * (size_t)cols, cudaMemcpyHostToDevice, h->stream);
+    link_to_dev_kernel<<<blocks_for(cols * KPV, 256), 256, 0, h->stream>>>(tmp, rows, KPV, cols, *out);
+    ++h->launches;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(SGL_ECUDA, "link upload: %s", cudaGetErrorString(e));
+    return SGL_OK;
+}
+
+int sgl_linked_nmf(sgl_handle* h, const sgl_csc* A_, const sgl_csc* At_, double tol, uint16_t maxit, double L1, double L2, int k,
+                   double* w, double* d, double* h_out, const double* link_h, int lh_rows, int64_t lh_cols, const double* link_w,
+                   int lw_rows, int64_t lw_cols, int32_t* iters_out, double* tol_out, const sgl_callbacks* cb) {
+    if (!h || !w || !d || !h_out) return fail(SGL_EINVAL, "sgl_linked_nmf: NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    sgl_matrix *A = nullptr, *At = nullptr;
+    SGL_TRY(cached_upload(h, A_, 1, &h->cA, &h->cmA, &A));
+    SGL_TRY(cached_upload(h, At_, 1, &h->cAt, &h->cmAt, &At));
+    SGL_TRY(check_shapes(A, At));
+    // src/singlet.cpp:1066-1067: a side is linked only when its matrix has one column per cell / gene
+    const bool linking_h = link_h && lh_cols == A->ncol, linking_w = link_w && lw_cols == A->nrow;
+    float *dlh = nullptr, *dlw = nullptr;
+    int rc = SGL_OK;
+    if (linking_h) rc = link_upload(h, link_h, lh_rows, lh_cols, k, &dlh);
+    if (rc == SGL_OK && linking_w) rc = link_upload(h, link_w, lw_rows, lw_cols, k, &dlw);
+    FitBuffers fb;
+    if (rc == SGL_OK) rc = fit_init(h, fb, k, A->nrow, A->ncol, w);
+    double tol_ = 1;
+    uint16_t iter_ = 0;
+    for (; rc == SGL_OK && iter_ < maxit && tol_ > tol; ++iter_) {  // src/singlet.cpp:1075
+        rc = als_iteration(h, fb, A, At, nullptr, nullptr, k, L1, L1, L2, L2, cb, &tol_, dlh, dlw);
+        if (rc == SGL_OK && cb && cb->on_iter) cb->on_iter(cb->user, iter_ + 1, tol_, NAN);
+        if (rc == SGL_OK && cb && cb->poll_interrupt && cb->poll_interrupt(cb->user)) rc = fail(SGL_EINTERRUPT, "interrupted");
+    }
+    if (rc == SGL_OK) {
+        if (iters_out) *iters_out = iter_;
+        if (tol_out) *tol_out = tol_;
+        rc = fit_outputs(h, fb, k, A->nrow, A->ncol, w, d, h_out);
+    }
+    if (dlh) cudaFree(dlh);
+    if (dlw) cudaFree(dlw);
+    return rc;
 }
 
 // ---- c_ard_nmf -----------------------------------------------------------------------------

@@ -115,6 +115,28 @@ __global__ void sum_splits_kernel(const float* __restrict__ parts, int splits, i
     }
 }
 
+// predict_link (src/singlet.cpp:429-430): out[c][f] = (sum over splits of parts[s][c][f]) * link[c][f]
+// (link is float [cols][KP] with 1.0 in the rows beyond link_rows)
+__global__ void link_rhs_kernel(const float* __restrict__ parts, int splits, int64_t n, const float* __restrict__ link,
+                                float* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) {
+        float s = 0.f;
+        for (int q = 0; q < splits; ++q) s += parts[(int64_t)q * n + e];
+        out[e] = s * link[e];
+    }
+}
+// link matrix (double, link_rows x cols column-major) -> float [cols][KP], rows >= link_rows = 1
+__global__ void link_to_dev_kernel(const double* __restrict__ src, int link_rows, int KP, int64_t cols,
+                                   float* __restrict__ dst) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < cols * KP) {
+        const int64_t c = e / KP;
+        const int f = (int)(e % KP);
+        dst[e] = (f < link_rows) ? (float)src[c * link_rows + f] : 1.f;
+    }
+}
+
 // cor (src/singlet.cpp:184-197): five running sums in FP64 -> per-CTA partials [grid][5]
 __global__ void __launch_bounds__(256)
 cor_partial_kernel(const float* __restrict__ X, const float* __restrict__ Y, int64_t n_elems,

