@@ -109,6 +109,16 @@ int sgl_ard_nmf(sgl_handle* h, const sgl_csc* A, int nA, const sgl_csc* At, int 
                 uint64_t inv_density, double overfit_threshold, uint16_t trace_test_mse, sgl_trace* trace,
                 const sgl_callbacks* cb);
 
+/* Dense-input variants c_nmf_dense / c_ard_nmf_dense: src/singlet.cpp:1051-1054, 1357-1361 (RcppExports.cpp:241-260,
+ * 329-350) with predict / predict_mask / mse_test on Eigen::MatrixXd (:370-381, 506-531, 610-634). A is m x n, At is
+ * n x m, column-major doubles. Every entry (zeros included) takes part, no column is skipped -- like the reference. */
+int sgl_nmf_dense(sgl_handle* h, const double* A, const double* At, int64_t m, int64_t n, double tol, uint16_t maxit,
+                  double L1_w, double L1_h, double L2_w, double L2_h, int k, double* w, double* d, double* h_out,
+                  int32_t* iters_out, double* tol_out, const sgl_callbacks* cb);
+int sgl_ard_nmf_dense(sgl_handle* h, const double* A, const double* At, int64_t m, int64_t n, double tol, uint16_t maxit,
+                      double L1, double L2, int k, double* w, double* d, double* h_out, uint64_t seed, uint64_t inv_density,
+                      double overfit_threshold, uint16_t trace_test_mse, sgl_trace* trace, const sgl_callbacks* cb);
+
 /* c_project_model: src/singlet.cpp:405-413 (RcppExports.cpp:82-95). w is w_rows x w_cols column-major;
  * it is transposed when w_rows == nrow(A) exactly as the reference does. h: k x n out, d: k out. */
 int sgl_project_model(sgl_handle* h, const sgl_csc* A, int nA, const double* w, int64_t w_rows, int64_t w_cols,

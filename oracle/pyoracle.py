@@ -97,6 +97,10 @@ class Oracle:
         f("project_model", None, [vp, i32, vp, i32, dbl, dbl, i32, vp, vp])
         f("linked_nmf", i32, [vp, vp, dbl, C.c_uint16, dbl, dbl, i32, i32, vp, vp, vp, vp, i32, i64, vp, i32, i64])
         f("max_threads", i32, [])
+        if kind == "reference":
+            f("nmf_dense", i32, [vp, vp, i64, i64, dbl, C.c_uint16, dbl, dbl, dbl, dbl, i32, i32, vp, vp, vp])
+            f("ard_nmf_dense", i32, [vp, vp, i64, i64, dbl, C.c_uint16, dbl, dbl, i32, i32, vp, vp, vp, u64, u64, dbl, C.c_uint16,
+                                     vp, vp, i32, vp])
         if kind == "port":
             f("mse_train", dbl, [vp, i32, vp, vp, vp, i32, u64, u64, i32])
             f("weight_by_split", None, [vp, vp, vp, i32])
@@ -222,6 +226,48 @@ class Oracle:
         q = nt.value
         return {"w": w, "d": d, "h": h, "test_mse": mse[:q].copy(), "iter": it[:q].copy(), "tol": ft[:q].copy(),
                 "score_overfit": so[:q].copy(), "last_iter": last}
+
+    @staticmethod
+    def _full_csc(D):
+        """Dense matrix -> CSC with EVERY entry stored (explicit zeros): the dense reference loops visit all rows."""
+        import scipy.sparse as sp
+
+        D = np.asfortranarray(D, np.float64)
+        m, n = D.shape
+        return sp.csc_matrix((D.ravel(order="F"), np.tile(np.arange(m, dtype=np.int32), n), np.arange(n + 1, dtype=np.int32) * m),
+                             shape=(m, n))
+
+    def nmf_dense(self, A, At, w_init, tol=1e-4, maxit=100, L1=(0.01, 0.01), L2=(0.0, 0.0), threads=0):
+        """c_nmf_dense (src/singlet.cpp:1051-1054). Port: the sparse restatement on the fully stored matrix (same
+        operations in the same order); reference: the reference's own dense code path."""
+        if self.kind == "port":
+            return self.nmf(self._full_csc(A), self._full_csc(At), w_init, tol, maxit, L1, L2, threads)
+        A = np.asfortranarray(A, np.float64)
+        At = np.asfortranarray(At, np.float64)
+        w = np.array(w_init, np.float64, order="F")
+        k, m = w.shape
+        n = A.shape[1]
+        d, h = np.zeros(k), np.zeros((k, n), order="F")
+        self._nmf_dense(_dp(A), _dp(At), m, n, tol, maxit, L1[0], L1[1], L2[0], L2[1], threads, k, _dp(w), _dp(d), _dp(h))
+        return {"w": w, "d": d, "h": h}
+
+    def ard_nmf_dense(self, A, At, w_init, seed, inv_density, tol=1e-4, maxit=100, L1=0.01, L2=0.0, threads=0,
+                      overfit_threshold=1e-4, trace_test_mse=5):
+        """c_ard_nmf_dense (src/singlet.cpp:1357-1361)."""
+        if self.kind == "port":
+            return self.ard_nmf(self._full_csc(A), self._full_csc(At), w_init, seed, inv_density, tol, maxit, L1, L2, threads,
+                                overfit_threshold, trace_test_mse)
+        A = np.asfortranarray(A, np.float64)
+        At = np.asfortranarray(At, np.float64)
+        w = np.array(w_init, np.float64, order="F")
+        k, m = w.shape
+        n = A.shape[1]
+        d, h = np.zeros(k), np.zeros((k, n), order="F")
+        cap = int(maxit) + 2
+        mse, it, nt = np.zeros(cap), np.zeros(cap, np.int32), C.c_int(0)
+        self._ard_nmf_dense(_dp(A), _dp(At), m, n, tol, maxit, L1, L2, threads, k, _dp(w), _dp(d), _dp(h), seed, inv_density,
+                            overfit_threshold, trace_test_mse, _dp(mse), _dp(it), cap, C.addressof(nt))
+        return {"w": w, "d": d, "h": h, "test_mse": mse[: nt.value].copy(), "iter": it[: nt.value].copy()}
 
     def linked_nmf(self, A, At, w_init, link_h, link_w, tol=1e-4, maxit=100, L1=0.01, L2=0.0, threads=0):
         """c_linked_nmf: link_h / link_w are (rows x cols) matrices; a side is linked only when its matrix has one

@@ -180,6 +180,38 @@ void ref_project_model(const orc_csc* A, int, double* w, int k, double L1, doubl
     put(out, "d", d);
 }
 
+// dense-input variants: A is m x n, At is n x m, both column-major
+int ref_nmf_dense(const double* A, const double* At, int64_t m, int64_t n, double tol, uint16_t maxit, double L1_w, double L1_h,
+                  double L2_w, double L2_h, int threads, int k, double* w, double* d, double* h) {
+    Eigen::MatrixXd a = mat(A, (long)m, (long)n), at = mat(At, (long)n, (long)m), wm = mat(w, k, (long)m);
+    Rcpp::List out = c_nmf_dense(a, at, tol, maxit, false, L1_w, L1_h, L2_w, L2_h, (uint16_t)threads_or_all(threads), wm);
+    put(out, "w", w);
+    put(out, "d", d);
+    put(out, "h", h);
+    return -1;
+}
+int ref_ard_nmf_dense(const double* A, const double* At, int64_t m, int64_t n, double tol, uint16_t maxit, double L1, double L2,
+                      int threads, int k, double* w, double* d, double* h, uint64_t seed, uint64_t inv_density,
+                      double overfit_threshold, uint16_t trace_test_mse, double* test_mse, int32_t* iter_out, int trace_cap,
+                      int* n_trace) {
+    Eigen::MatrixXd a = mat(A, (long)m, (long)n), at = mat(At, (long)n, (long)m), wm = mat(w, k, (long)m);
+    Rcpp::List out = c_ard_nmf_dense(a, at, tol, maxit, false, L1, L2, (uint16_t)threads_or_all(threads), wm, seed, inv_density,
+                                     overfit_threshold, trace_test_mse);
+    put(out, "w", w);
+    put(out, "d", d);
+    put(out, "h", h);
+    const Rcpp::Entry* e = out.find("test_mse");
+    const Rcpp::Entry* ei = out.find("iter");
+    int nt = e ? (int)e->data.size() : 0;
+    if (nt > trace_cap) nt = trace_cap;
+    for (int q = 0; q < nt; ++q) {
+        test_mse[q] = e->data[(size_t)q];
+        iter_out[q] = (int32_t)ei->data[(size_t)q];
+    }
+    *n_trace = nt;
+    return nt;
+}
+
 int ref_linked_nmf(const orc_csc* A, const orc_csc* At, double tol, uint16_t maxit, double L1, double L2, int threads, int k,
                    double* w, double* d, double* h, const double* link_h, int lh_rows, int64_t lh_cols, const double* link_w,
                    int lw_rows, int64_t lw_cols) {

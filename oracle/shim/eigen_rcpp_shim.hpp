@@ -231,6 +231,15 @@ inline void TriangularProxy<UpLo>::operator=(const TransposeOf& t) {
         for (long i = 0; i <= j; ++i) (*m)(i, j) = s(j, i);
 }
 
+// dense matrix-vector product (predict on dense input: `b = w * A.col(i)`), accumulated column by column
+inline VectorXd operator*(const MatrixXd& M, const ConstColRef& c) {
+    VectorXd out(M.rows());
+    for (long j = 0; j < M.cols(); ++j)
+        for (long i = 0; i < M.rows(); ++i) out(i) += c.ptr[j] * M(i, j);
+    return out;
+}
+inline VectorXd operator*(const MatrixXd& M, const ColAssign& c) { return M * ConstColRef{c.ptr, c.n}; }
+
 inline MatrixXd operator-(const MatrixXd& a, const MatrixXd& b) {
     MatrixXd out(a.rows(), a.cols());
     for (size_t t = 0; t < out.v.size(); ++t) out.v[t] = a.v[t] - b.v[t];

@@ -125,6 +125,45 @@ Rcpp::List c_nmf_sparse_list(Rcpp::List A_, Rcpp::List& At_, const double tol, c
     return nmf_impl(views(A), views(At), tol, maxit, verbose, L1, L1, L2, L2, w);
 }
 
+// dense-input variants (reference src/singlet.cpp:1051-1054, 1357-1361): R matrices are column-major doubles
+//[[Rcpp::export]]
+Rcpp::List c_nmf_dense(Eigen::MatrixXd& A, Eigen::MatrixXd& At, const double tol, const uint16_t maxit, const bool verbose,
+                       const double L1_w, const double L1_h, const double L2_w, const double L2_h, const uint16_t threads,
+                       Eigen::MatrixXd w) {
+    const int k = (int)w.rows();
+    Eigen::MatrixXd h(k, A.cols());
+    Eigen::VectorXd d(k);
+    Progress p{verbose, false};
+    sgl_callbacks cb = callbacks(p);
+    if (verbose) Rprintf("\n%4s | %8s \n---------------\n", "iter", "tol");
+    check(sgl_nmf_dense(handle(), A.data(), At.data(), A.rows(), A.cols(), tol, maxit, L1_w, L1_h, L2_w, L2_h, k, w.data(), d.data(),
+                        h.data(), nullptr, nullptr, &cb));
+    return Rcpp::List::create(Rcpp::Named("w") = w, Rcpp::Named("d") = d, Rcpp::Named("h") = h);
+}
+
+//[[Rcpp::export]]
+Rcpp::List c_ard_nmf_dense(Eigen::MatrixXd& A, Eigen::MatrixXd& At, const double tol, const uint16_t maxit, const bool verbose,
+                           const double L1, const double L2, const uint16_t threads, Eigen::MatrixXd w, const uint64_t seed,
+                           const uint64_t inv_density, const double overfit_threshold, const uint16_t trace_test_mse) {
+    const int k = (int)w.rows();
+    Eigen::MatrixXd h(k, A.cols());
+    Eigen::VectorXd d(k);
+    const int cap = (int)maxit + 2;
+    std::vector<double> mse(cap), ft(cap), so(cap);
+    std::vector<int32_t> it(cap);
+    sgl_trace tr{mse.data(), it.data(), ft.data(), so.data(), cap, 0};
+    Progress p{verbose, true};
+    sgl_callbacks cb = callbacks(p);
+    if (verbose) Rprintf("\n%4s | %8s | %8s \n---------------------------\n", "iter", "tol", "overfit");
+    check(sgl_ard_nmf_dense(handle(), A.data(), At.data(), A.rows(), A.cols(), tol, maxit, L1, L2, k, w.data(), d.data(), h.data(), seed,
+                            inv_density, overfit_threshold, trace_test_mse, &tr, &cb));
+    Rcpp::NumericVector test_mse(mse.begin(), mse.begin() + tr.length), fit_tol(ft.begin(), ft.begin() + tr.length),
+        score(so.begin(), so.begin() + tr.length);
+    Rcpp::IntegerVector iter(it.begin(), it.begin() + tr.length);
+    return Rcpp::List::create(Rcpp::Named("w") = w, Rcpp::Named("d") = d, Rcpp::Named("h") = h, Rcpp::Named("test_mse") = test_mse,
+                              Rcpp::Named("iter") = iter, Rcpp::Named("tol") = fit_tol, Rcpp::Named("score_overfit") = score);
+}
+
 // "next" row f2: linked NMF (reference src/singlet.cpp:1059-1086, called by R/RunLNMF.R:60)
 //[[Rcpp::export]]
 Rcpp::List c_linked_nmf(Rcpp::SparseMatrix A, Rcpp::SparseMatrix At, const double tol, const uint16_t maxit, const bool verbose,

@@ -5,7 +5,7 @@ Importing the package never touches the GPU; the shared library ``libsinglet_cud
 first use and there is no CPU fallback (``SingletCudaError`` is raised instead).
 """
 from ._lib import SingletCudaError  # noqa: F401
-from .api import (GetBestRank, Handle, Rcpp_predict, ard_nmf, c_ard_nmf, c_ard_nmf_sparse_list, c_linked_nmf, c_nmf,  # noqa: F401
+from .api import (GetBestRank, Handle, Rcpp_predict, ard_nmf, c_ard_nmf, c_ard_nmf_dense, c_ard_nmf_sparse_list, c_linked_nmf, c_nmf, c_nmf_dense,  # noqa: F401
                   c_nmf_sparse_list, c_project_model, weight_by_split, cross_validate_nmf, default_handle, project_model, run_nmf, set_seed)
 from .datasets import get_pbmc3k_data, log_normalize  # noqa: F401
 

@@ -62,6 +62,9 @@ SYMBOLS = [
                               _vp, _vp]),
     ("sgl_ard_nmf", _i32, [_vp, _vp, _i32, _vp, _i32, _dbl, _u16, _dbl, _dbl, _i32, _vp, _vp, _vp, _u64, _u64, _dbl, _u16,
                            _vp, _vp]),
+    ("sgl_nmf_dense", _i32, [_vp, _vp, _vp, _i64, _i64, _dbl, _u16, _dbl, _dbl, _dbl, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("sgl_ard_nmf_dense", _i32, [_vp, _vp, _vp, _i64, _i64, _dbl, _u16, _dbl, _dbl, _i32, _vp, _vp, _vp, _u64, _u64, _dbl, _u16,
+                                 _vp, _vp]),
     ("sgl_project_model", _i32, [_vp, _vp, _i32, _vp, _i64, _i64, _dbl, _dbl, _vp, _vp]),
     ("sgl_predict", _i32, [_vp, _vp, _i32, _vp, _i64, _i64, _dbl, _dbl, _vp]),
     ("sgl_mask_rand", _i32, [_vp, _u64, _vp, _vp, _i64, _vp]),

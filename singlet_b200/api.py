@@ -172,6 +172,49 @@ def c_nmf_sparse_list(A_, At_, tol, maxit, verbose, L1, L2, threads, w, handle: 
     return c_nmf(list(A_), list(At_), tol, maxit, verbose, L1, L1, L2, L2, threads, w, handle)
 
 
+def c_nmf_dense(A, At, tol, maxit, verbose, L1_w, L1_h, L2_w, L2_h, threads, w, handle: Handle | None = None):
+    """``c_nmf_dense`` (reference src/singlet.cpp:1051-1054; R/RcppExports.R:70-72): A (m x n) and At (n x m) are
+    dense numpy matrices."""
+    h = handle or default_handle()
+    Ad, Atd = np.asfortranarray(A, dtype=np.float64), np.asfortranarray(At, dtype=np.float64)
+    wk = np.array(w, dtype=np.float64, order="F")
+    k, m = wk.shape
+    n = Ad.shape[1]
+    if Ad.shape[0] != m or Atd.shape != (n, m):
+        raise ValueError("shapes of A, At and w do not agree")
+    d, hh = np.zeros(k), np.zeros((k, n), order="F")
+    iters, ftol = C.c_int32(0), C.c_double(0)
+    cb, keep = _callbacks(bool(verbose), False)
+    _lib.check(h.lib.sgl_nmf_dense(h.ptr, _dp(Ad), _dp(Atd), m, n, float(tol), int(maxit) & 0xFFFF, float(L1_w), float(L1_h),
+                                   float(L2_w), float(L2_h), k, _dp(wk), _dp(d), _dp(hh), C.addressof(iters), C.addressof(ftol),
+                                   C.addressof(cb) if cb is not None else None))
+    return {"w": wk, "d": d, "h": hh, "iter": iters.value, "tol": ftol.value}
+
+
+def c_ard_nmf_dense(A, At, tol, maxit, verbose, L1, L2, threads, w, seed, inv_density, overfit_threshold, trace_test_mse,
+                    handle: Handle | None = None):
+    """``c_ard_nmf_dense`` (reference src/singlet.cpp:1357-1361; R/RcppExports.R:86-88)."""
+    h = handle or default_handle()
+    Ad, Atd = np.asfortranarray(A, dtype=np.float64), np.asfortranarray(At, dtype=np.float64)
+    wk = np.array(w, dtype=np.float64, order="F")
+    k, m = wk.shape
+    n = Ad.shape[1]
+    if Ad.shape[0] != m or Atd.shape != (n, m):
+        raise ValueError("shapes of A, At and w do not agree")
+    d, hh = np.zeros(k), np.zeros((k, n), order="F")
+    cap = (int(maxit) & 0xFFFF) + 2
+    mse, ft, so, it = np.zeros(cap), np.zeros(cap), np.zeros(cap), np.zeros(cap, np.int32)
+    tr = _lib.Trace(mse.ctypes.data, it.ctypes.data, ft.ctypes.data, so.ctypes.data, cap, 0)
+    cb, keep = _callbacks(bool(verbose), True)
+    _lib.check(h.lib.sgl_ard_nmf_dense(h.ptr, _dp(Ad), _dp(Atd), m, n, float(tol), int(maxit) & 0xFFFF, float(L1), float(L2), k,
+                                       _dp(wk), _dp(d), _dp(hh), int(seed) & 0xFFFFFFFFFFFFFFFF, int(inv_density),
+                                       float(overfit_threshold), int(trace_test_mse) & 0xFFFF, C.addressof(tr),
+                                       C.addressof(cb) if cb is not None else None))
+    q = tr.length
+    return {"w": wk, "d": d, "h": hh, "test_mse": mse[:q].copy(), "iter": it[:q].copy(), "tol": ft[:q].copy(),
+            "score_overfit": so[:q].copy()}
+
+
 def c_linked_nmf(A, At, tol, maxit, verbose, L1, L2, threads, w, link_h, link_w, handle: Handle | None = None):
     """``c_linked_nmf`` (reference src/singlet.cpp:1059-1086; R/RcppExports.R:74-76): ALS NMF where ``b`` is
     multiplied by a column of ``link_h`` / ``link_w`` before every solve (``predict_link`` :416-433). A side is

@@ -348,6 +348,36 @@ static int build_stream(sgl_handle* h, const sgl_matrix* m, const TileIndex& ti,
     return SGL_OK;
 }
 
+// dense m x n column-major doubles -> device matrix with every entry stored
+static int matrix_from_dense(sgl_handle* h, const double* D, int64_t nrow, int64_t ncol, sgl_matrix** out) {
+    if (!D || nrow < 1 || ncol < 0 || nrow > 0x7fffffffLL) return fail(SGL_EINVAL, "dense upload: bad argument");
+    SGL_TRY(set_device(h));
+    sgl_matrix* m = new sgl_matrix();
+    m->nrow = nrow;
+    m->ncol = ncol;
+    m->nnz = nrow * ncol;
+    double* tmp = nullptr;
+    const size_t n = (size_t)(m->nnz > 0 ? m->nnz : 1);
+    if (cudaMalloc(&m->colptr, sizeof(int64_t) * (size_t)(ncol + 1)) != cudaSuccess || cudaMalloc(&m->rec, sizeof(uint2) * n) != cudaSuccess ||
+        cudaMalloc(&tmp, sizeof(double) * n) != cudaSuccess) {
+        if (tmp) cudaFree(tmp);
+        matrix_release(m);
+        return fail(SGL_ENOMEM, "dense upload: cudaMalloc failed");
+    }
+    cudaMemcpyAsync(tmp, D, sizeof(double) * (size_t)m->nnz, cudaMemcpyHostToDevice, h->stream);
+    const int64_t work = m->nnz > ncol + 1 ? m->nnz : ncol + 1;
+    dense_to_records_kernel<<<blocks_for(work, 256), 256, 0, h->stream>>>(tmp, nrow, ncol, m->rec, m->colptr);
+    ++h->launches;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) {
+        matrix_release(m);
+        return fail(SGL_ECUDA, "dense upload: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return SGL_OK;
+}
+
 // tile index for padded rank KP (lazily built, cached on the matrix)
 static int get_tiles(sgl_handle* h, sgl_matrix* m, int kpv, const TileIndex** out) {
     auto it = m->tiles.find(kpv);
@@ -979,6 +1009,13 @@ int sgl_profile_read(sgl_handle* h, double* ms, int64_t* counts, int64_t* bytes)
 }
 
 // ---- c_nmf ---------------------------------------------------------------------------------
+static int nmf_on_device(sgl_handle* h, sgl_matrix* A, sgl_matrix* At, double tol, uint16_t maxit, double L1_w, double L1_h,
+                         double L2_w, double L2_h, int k, double* w, double* d, double* h_out, int32_t* iters_out, double* tol_out,
+                         const sgl_callbacks* cb);
+static int ard_on_device(sgl_handle* h, sgl_matrix* A, sgl_matrix* At, double tol, uint16_t maxit, double L1, double L2, int k, double* w,
+                         double* d, double* h_out, uint64_t seed, uint64_t inv_density, double overfit_threshold,
+                         uint16_t trace_test_mse, sgl_trace* tr, const sgl_callbacks* cb);
+
 int sgl_nmf(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, int nAt, double tol, uint16_t maxit, double L1_w,
             double L1_h, double L2_w, double L2_h, int k, double* w, double* d, double* h_out, int32_t* iters_out,
             double* tol_out, const sgl_callbacks* cb) {
@@ -988,6 +1025,71 @@ int sgl_nmf(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, int nA
     sgl_matrix *A = nullptr, *At = nullptr;
     SGL_TRY(cached_upload(h, A_, nA, &h->cA, &h->cmA, &A));
     SGL_TRY(cached_upload(h, At_, nAt, &h->cAt, &h->cmAt, &At));
+    return nmf_on_device(h, A, At, tol, maxit, L1_w, L1_h, L2_w, L2_h, k, w, d, h_out, iters_out, tol_out, cb);
+}
+
+// dense uploads share the handle's cache slots (keyed by pointer, shape and a content sample)
+static int cached_dense(sgl_handle* h, const double* D, int64_t nrow, int64_t ncol, sgl_matrix** slot, sgl_mask** mask_slot,
+                        sgl_matrix** out) {
+    if (!D) return fail(SGL_EINVAL, "dense matrix is NULL");
+    uint64_t fp = splitmix64(0xD3115Eull ^ (uint64_t)(uintptr_t)D);
+    fp = splitmix64(fp ^ (uint64_t)nrow);
+    fp = splitmix64(fp ^ ((uint64_t)ncol << 1));
+    const int64_t tot = nrow * ncol, step = tot > 4096 ? tot / 4096 : 1;
+    for (int64_t t = 0; t < tot; t += step) {
+        uint64_t bits;
+        std::memcpy(&bits, &D[t], 8);
+        fp = splitmix64(fp ^ bits);
+    }
+    if (h->cache && *slot && (*slot)->fingerprint == fp) {
+        *out = *slot;
+        return SGL_OK;
+    }
+    if (*mask_slot) {
+        mask_release(*mask_slot);
+        *mask_slot = nullptr;
+    }
+    if (*slot) {
+        matrix_release(*slot);
+        *slot = nullptr;
+    }
+    sgl_matrix* m = nullptr;
+    SGL_TRY(matrix_from_dense(h, D, nrow, ncol, &m));
+    m->fingerprint = fp;
+    *slot = m;
+    *out = m;
+    return SGL_OK;
+}
+
+int sgl_nmf_dense(sgl_handle* h, const double* A_, const double* At_, int64_t m, int64_t n, double tol, uint16_t maxit, double L1_w,
+                  double L1_h, double L2_w, double L2_h, int k, double* w, double* d, double* h_out, int32_t* iters_out,
+                  double* tol_out, const sgl_callbacks* cb) {
+    if (!h || !w || !d || !h_out) return fail(SGL_EINVAL, "sgl_nmf_dense: NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    sgl_matrix *A = nullptr, *At = nullptr;
+    SGL_TRY(cached_dense(h, A_, m, n, &h->cA, &h->cmA, &A));
+    SGL_TRY(cached_dense(h, At_, n, m, &h->cAt, &h->cmAt, &At));
+    return nmf_on_device(h, A, At, tol, maxit, L1_w, L1_h, L2_w, L2_h, k, w, d, h_out, iters_out, tol_out, cb);
+}
+
+int sgl_ard_nmf_dense(sgl_handle* h, const double* A_, const double* At_, int64_t m, int64_t n, double tol, uint16_t maxit, double L1,
+                      double L2, int k, double* w, double* d, double* h_out, uint64_t seed, uint64_t inv_density,
+                      double overfit_threshold, uint16_t trace_test_mse, sgl_trace* tr, const sgl_callbacks* cb) {
+    if (!h || !w || !d || !h_out || !tr) return fail(SGL_EINVAL, "sgl_ard_nmf_dense: NULL argument");
+    if (trace_test_mse == 0) return fail(SGL_EINVAL, "trace_test_mse must be >= 1 (the reference divides by it)");
+    if (inv_density == 0) return fail(SGL_EINVAL, "inv_density must be >= 1");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    sgl_matrix *A = nullptr, *At = nullptr;
+    SGL_TRY(cached_dense(h, A_, m, n, &h->cA, &h->cmA, &A));
+    SGL_TRY(cached_dense(h, At_, n, m, &h->cAt, &h->cmAt, &At));
+    return ard_on_device(h, A, At, tol, maxit, L1, L2, k, w, d, h_out, seed, inv_density, overfit_threshold, trace_test_mse, tr, cb);
+}
+
+static int nmf_on_device(sgl_handle* h, sgl_matrix* A, sgl_matrix* At, double tol, uint16_t maxit, double L1_w, double L1_h,
+                         double L2_w, double L2_h, int k, double* w, double* d, double* h_out, int32_t* iters_out, double* tol_out,
+                         const sgl_callbacks* cb) {
     SGL_TRY(check_shapes(A, At));
     FitBuffers fb;
     SGL_TRY(fit_init(h, fb, k, A->nrow, A->ncol, w));
@@ -1066,6 +1168,12 @@ int sgl_ard_nmf(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, in
     sgl_matrix *A = nullptr, *At = nullptr;
     SGL_TRY(cached_upload(h, A_, nA, &h->cA, &h->cmA, &A));
     SGL_TRY(cached_upload(h, At_, nAt, &h->cAt, &h->cmAt, &At));
+    return ard_on_device(h, A, At, tol, maxit, L1, L2, k, w, d, h_out, seed, inv_density, overfit_threshold, trace_test_mse, tr, cb);
+}
+
+static int ard_on_device(sgl_handle* h, sgl_matrix* A, sgl_matrix* At, double tol, uint16_t maxit, double L1, double L2, int k, double* w,
+                         double* d, double* h_out, uint64_t seed, uint64_t inv_density, double overfit_threshold,
+                         uint16_t trace_test_mse, sgl_trace* tr, const sgl_callbacks* cb) {
     SGL_TRY(check_shapes(A, At));
     sgl_mask *mA = nullptr, *mAt = nullptr;
     SGL_TRY(cached_mask(h, A, seed, inv_density, 0, &h->cmA, &mA));

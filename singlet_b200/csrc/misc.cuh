@@ -181,6 +181,15 @@ __global__ void colptr_from_p32_kernel(const int32_t* __restrict__ p, int64_t nc
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < ncol_chunk + (last ? 1 : 0)) colptr[c] = nnz_offset + (int64_t)p[c];
 }
+// dense-input variants (src/singlet.cpp:370-381, 506-531, 610-634): the dense loops visit EVERY row of a column,
+// zeros included, and never skip a column; storing every entry as a record reproduces exactly that.
+__global__ void dense_to_records_kernel(const double* __restrict__ D, int64_t nrow, int64_t ncol, uint2* __restrict__ rec,
+                                        int64_t* __restrict__ colptr) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nrow * ncol) rec[e] = make_uint2((uint32_t)(e % nrow), __float_as_uint((float)D[e]));
+    if (e <= ncol) colptr[e] = e * nrow;
+}
+
 // double k x cols column-major (element (f,c) at c*k+f) -> float [cols][KP], zero padded
 __global__ void factor_to_dev_kernel(const double* __restrict__ src, int k, int KP, int64_t cols,
                                      float* __restrict__ dst) {

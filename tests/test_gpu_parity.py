@@ -343,3 +343,22 @@ def test_weight_by_split_matches_oracle(oracle):
     assert np.allclose(got.data, exp, rtol=1e-14)
     sums = np.bincount(np.repeat(split, np.diff(got.indptr)), weights=got.data, minlength=3)
     assert np.allclose(sums, sums[0])
+
+
+def test_dense_variants_match_oracle(handle, oracle):
+    """c_nmf_dense / c_ard_nmf_dense (row a15 of SURVEY.md 8): dense numpy input through the C ABI."""
+    from singlet_b200 import api, synth
+
+    rs = np.random.RandomState(5)
+    m, n, k = 220, 160, 5
+    D = np.where(rs.rand(m, n) > 0.7, rs.rand(m, n) * 3, 0.0)
+    D[:, 3] = 0
+    Dt = np.ascontiguousarray(D.T)
+    w0 = synth.w_init(k, m, seed=2)
+    dev = api.c_nmf_dense(D, Dt, 0.0, 6, False, 0.01, 0.01, 0.0, 0.0, 0, w0)
+    ref = oracle.nmf_dense(D, Dt, w0, tol=0.0, maxit=6)
+    assert min_factor_cor(ref["w"], dev["w"]) >= COR_MIN and min_factor_cor(ref["h"], dev["h"]) >= COR_MIN
+    assert np.allclose(dev["d"], ref["d"], rtol=5e-3)
+    devm = api.c_ard_nmf_dense(D, Dt, 0.0, 5, False, 0.01, 0.0, 0, w0, 123, 10, 10.0, 2)
+    refm = oracle.ard_nmf_dense(D, Dt, w0, 123, 10, tol=0.0, maxit=5, overfit_threshold=10.0, trace_test_mse=2)
+    assert list(devm["iter"]) == list(refm["iter"]) and np.allclose(devm["test_mse"], refm["test_mse"], rtol=MSE_RTOL)

@@ -153,3 +153,21 @@ def test_linked_nmf_port_equals_reference(oracle, ref_oracle):
     assert np.array_equal(plain["h"], unl["h"])  # no matrix matches a dimension -> plain NMF
     zero_rows = np.nonzero(link_h[0] == 0)[0]
     assert np.all(a["h"][0, zero_rows] == 0) or True
+
+
+def test_dense_variants_port_equals_reference(oracle, ref_oracle):
+    """c_nmf_dense / c_ard_nmf_dense (src/singlet.cpp:1051-1054, 1357-1361 over :370-381, 506-531, 610-634): the
+    sparse restatement on a fully stored matrix reproduces the reference's dense code path bit for bit."""
+    from singlet_b200 import synth
+
+    rs = np.random.RandomState(0)
+    m, n, k = 60, 45, 4
+    D = np.where(rs.rand(m, n) > 0.6, rs.rand(m, n) * 3, 0.0)
+    D[:, 7] = 0  # an all-zero column is NOT skipped on the dense path
+    w0 = synth.w_init(k, m, seed=1)
+    a, b = oracle.nmf_dense(D, D.T.copy(), w0, maxit=7), ref_oracle.nmf_dense(D, D.T.copy(), w0, maxit=7)
+    for key in ("w", "d", "h"):
+        assert np.array_equal(a[key], b[key]), key
+    a = oracle.ard_nmf_dense(D, D.T.copy(), w0, 123, 5, maxit=6, trace_test_mse=2, overfit_threshold=10.0)
+    b = ref_oracle.ard_nmf_dense(D, D.T.copy(), w0, 123, 5, maxit=6, trace_test_mse=2, overfit_threshold=10.0)
+    assert np.array_equal(a["test_mse"], b["test_mse"]) and np.array_equal(a["iter"], b["iter"]) and np.array_equal(a["h"], b["h"])
