@@ -322,7 +322,19 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
         const int64_t zero = 0;
         cudaMemcpyAsync(m->colptr, &zero, sizeof(int64_t), cudaMemcpyHostToDevice, h->stream);
     }
+    int* d_flag = nullptr;
+    int bad = 0;
+    if (rc == SGL_OK && ncol > 0 && cudaMalloc(&d_flag, sizeof(int)) == cudaSuccess) {
+        cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream);
+        validate_records_kernel<<<blocks_for(ncol, 8), 256, 0, h->stream>>>(m->rec, m->colptr, ncol, nrow, d_flag);
+        ++h->launches;
+        cudaMemcpyAsync(&bad, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    }
     cudaError_t es = cudaStreamSynchronize(h->stream);
+    if (d_flag) cudaFree(d_flag);
+    if (rc == SGL_OK && es == cudaSuccess && bad)
+        rc = fail(SGL_EINVAL, "matrix upload: %s%s%s", (bad & 1) ? "row index out of range" : "", (bad == 3) ? "; " : "",
+                  (bad & 2) ? "row indices not strictly ascending within a column (not a valid dgCMatrix)" : "");
     cudaFree(d_p);
     if (rc == SGL_OK && es != cudaSuccess) rc = fail(SGL_ECUDA, "matrix upload: %s", cudaGetErrorString(es));
     if (rc != SGL_OK) {

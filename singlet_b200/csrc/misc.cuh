@@ -181,6 +181,24 @@ __global__ void colptr_from_p32_kernel(const int32_t* __restrict__ p, int64_t nc
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < ncol_chunk + (last ? 1 : 0)) colptr[c] = nnz_offset + (int64_t)p[c];
 }
+// input validation after upload: rows in range and strictly ascending within every column (the tile index and the
+// shared-memory gather rely on it; a dgCMatrix guarantees it). flag[0] |= 1 (range) | 2 (order).
+__global__ void __launch_bounds__(256)
+validate_records_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ colptr, int64_t ncol, int64_t nrow,
+                        int* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t col = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (col >= ncol) return;
+    int bad = 0;
+    const int64_t b = colptr[col], e = colptr[col + 1];
+    for (int64_t t = b + lane; t < e; t += 32) {
+        const uint32_t r = rec[t].x;
+        if ((int64_t)r >= nrow) bad |= 1;
+        if (t + 1 < e && rec[t + 1].x <= r) bad |= 2;
+    }
+    if (bad) atomicOr(flag, bad);
+}
+
 // dense-input variants (src/singlet.cpp:370-381, 506-531, 610-634): the dense loops visit EVERY row of a column,
 // zeros included, and never skip a column; storing every entry as a record reproduces exactly that.
 __global__ void dense_to_records_kernel(const double* __restrict__ D, int64_t nrow, int64_t ncol, uint2* __restrict__ rec,

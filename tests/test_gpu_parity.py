@@ -362,3 +362,47 @@ def test_dense_variants_match_oracle(handle, oracle):
     devm = api.c_ard_nmf_dense(D, Dt, 0.0, 5, False, 0.01, 0.0, 0, w0, 123, 10, 10.0, 2)
     refm = oracle.ard_nmf_dense(D, Dt, w0, 123, 10, tol=0.0, maxit=5, overfit_threshold=10.0, trace_test_mse=2)
     assert list(devm["iter"]) == list(refm["iter"]) and np.allclose(devm["test_mse"], refm["test_mse"], rtol=MSE_RTOL)
+
+
+def test_invalid_matrix_and_interrupt(handle):
+    """Bad dgCMatrix input is rejected with SGL_EINVAL instead of faulting; poll_interrupt aborts a fit with
+    SGL_EINTERRUPT (the Rcpp::checkUserInterrupt points of src/singlet.cpp:652,663) and on_iter sees every iteration."""
+    import ctypes as C
+
+    from singlet_b200 import SingletCudaError, _lib, api, synth
+
+    A, At = _mk(120, 80, 0.2, seed=4)
+    w0 = synth.w_init(3, 120)
+    bad = A.copy()
+    bad.indices = bad.indices.copy()
+    lo, hi = bad.indptr[5], bad.indptr[6]
+    bad.indices[lo:hi] = bad.indices[lo:hi][::-1]  # descending rows in one column
+    bad.has_sorted_indices = True
+    with pytest.raises(SingletCudaError) as e:
+        api.c_nmf(bad, At, 1e-4, 2, False, 0, 0, 0, 0, 0, w0)
+    assert e.value.code == _lib.SGL_EINVAL and "ascending" in str(e.value)
+    oob = A.copy()
+    oob.indices = oob.indices.copy()
+    oob.indices[oob.indptr[3 + 1] - 1] = 5000
+    oob.has_sorted_indices = True
+    with pytest.raises(SingletCudaError) as e:
+        api.c_nmf(oob, At, 1e-4, 2, False, 0, 0, 0, 0, 0, w0)
+    assert "out of range" in str(e.value)
+
+    seen, polls = [], [0]
+
+    def on_iter(_u, it, tol, overfit):
+        seen.append((it, tol))
+
+    def poll(_u):
+        polls[0] += 1
+        return 1 if len(seen) >= 3 else 0
+
+    cb = _lib.Callbacks(None, _lib.POLL_FN(poll), _lib.ITER_FN(on_iter))
+    a, na, k1 = _lib.chunks_to_c(A)
+    at, nat, k2 = _lib.chunks_to_c(At)
+    w = np.array(w0, order="F")
+    d, h = np.zeros(3), np.zeros((3, 80), order="F")
+    rc = handle.lib.sgl_nmf(handle.ptr, a, na, at, nat, 0.0, 50, 0.01, 0.01, 0.0, 0.0, 3, w.ctypes.data, d.ctypes.data, h.ctypes.data,
+                            None, None, C.addressof(cb))
+    assert rc == _lib.SGL_EINTERRUPT and [s[0] for s in seen] == [1, 2, 3] and polls[0] >= 3
