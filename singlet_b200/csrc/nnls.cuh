@@ -363,23 +363,48 @@ nnls_masked_kernel(const float* __restrict__ Bparts, int splits, float* __restri
             if ((i & 31) == lane) inv[i / 32] = 1.0f / dia;
         }
 
+        // Coordinate loop. Every lane runs the (branch-free) scalar step on ITS OWN coordinate of slot i / 32 --
+        // only the owner lane's result is meaningful -- and one shuffle broadcasts the owner's multiplier, so a
+        // step costs one SHFL instead of three. The reference's running `tol` (reset to 1 by a clamp event, then
+        // accumulating the later terms, src/singlet.cpp:240-246) is rebuilt at the end of the sweep from the
+        // per-lane records: tol = [any event] + sum of the terms of the coordinates after the last event.
         float tol = 1.f;
         const float kf = (float)k;
         for (int sweep = 0; sweep < NNLS_MAX_SWEEPS && (tol / kf > 1e-8f); ++sweep) {
-            tol = 0.f;
+            float term[RPL];
+            bool ev[RPL];
+#pragma unroll
+            for (int c = 0; c < RPL; ++c) { term[c] = 0.f; ev[c] = false; }
 #pragma unroll
             for (int i = 0; i < KP; ++i) {
                 if (i < k) {  // uniform
                     const int owner = i & 31, c_own = i >> 5;
-                    const float bi = __shfl_sync(0xffffffffu, b[c_own], owner);
-                    float xi = __shfl_sync(0xffffffffu, x[c_own], owner);
-                    const float iv = __shfl_sync(0xffffffffu, inv[c_own], owner);
-                    const float delta = cd_step(bi, iv, xi, L1, L2, tol);  // redundantly on all lanes
-                    if (lane == owner) x[c_own] = xi;
+                    float xi = x[c_own];
+                    float t0 = 0.f;  // starts from 0: a clamp event leaves 1, a regular step leaves its term
+                    const float xold = xi;
+                    const float m_own = cd_step_nb(b[c_own], inv[c_own], xi, L1, L2, t0);
+                    const float mult = __shfl_sync(0xffffffffu, m_own, owner);
+                    if (lane == owner) {
+                        const bool clamp_ev = (xi == 0.f) && (xold != 0.f) && (t0 == 1.f);
+                        x[c_own] = xi;
+                        ev[c_own] = clamp_ev;
+                        term[c_own] = clamp_ev ? 0.f : t0;
+                    }
 #pragma unroll
-                    for (int c = 0; c < RPL; ++c) b[c] = fmaf(-a[c][i], delta, b[c]);
+                    for (int c = 0; c < RPL; ++c) b[c] = fmaf(a[c][i], mult, b[c]);
                 }
             }
+            // rebuild tol: position of the last clamp event in coordinate order i = 32 * c + lane
+            int last = -1;
+#pragma unroll
+            for (int c = 0; c < RPL; ++c) {
+                const uint32_t mk = __ballot_sync(0xffffffffu, ev[c]);
+                if (mk) last = 32 * c + (31 - __clz(mk));
+            }
+            float part = 0.f;
+#pragma unroll
+            for (int c = 0; c < RPL; ++c) part += (32 * c + lane > last) ? term[c] : 0.f;
+            tol = warp_sum(part) + (last >= 0 ? 1.f : 0.f);
         }
     }
 
