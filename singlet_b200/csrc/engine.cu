@@ -579,7 +579,7 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
     }
 #define NNLS_CASE(KPC)                                                                                              \
     case KPC:                                                                                                       \
-        if (ncol >= (int64_t)h->sm_count * NnlsCfg<KPC>::THREADS * 2) NNLS_LAUNCH(KPC, NnlsCfg<KPC>::THREADS, 2)   \
+        if (ncol >= (int64_t)h->sm_count * NnlsCfg<KPC>::THREADS * 2) NNLS_LAUNCH(KPC, NnlsCfg<KPC>::THREADS, NnlsCfg<KPC>::NCL) \
         else NNLS_LAUNCH(KPC, 32, 1)                                                                                \
         break;
                 NNLS_CASE(4) NNLS_CASE(8) NNLS_CASE(16) NNLS_CASE(32) NNLS_CASE(64)

@@ -47,8 +47,9 @@ __device__ __forceinline__ float cd_step(float bi, float inv_aii, float& xi, flo
 // ----------------------------------------------------------------------------------------------
 template <int KP>
 struct NnlsCfg {
-    static constexpr int THREADS = (KP <= 32) ? 128 : 64;
-    static constexpr int MIN_CTAS = (KP <= 32) ? 3 : 2;  // register cap: 170 (KP<=32) / 255 (KP=64)
+    static constexpr int THREADS = 128;
+    static constexpr int NCL = (KP <= 32) ? 2 : 1;  // columns per lane: 64 registers of right-hand sides either way
+    static constexpr int MIN_CTAS = 3;              // register cap 170
 };
 
 // branch-free coordinate step (same arithmetic as cd_step): returns MINUS the delta, i.e. the
