@@ -171,7 +171,12 @@ def cpu_reference_leg(cfg, steps, warmup, sample_cells, backend=None):
     per_iter = float(np.median(times[1:])) if len(times) > 1 else times[0]
     its_sample = 1.0 / per_iter
     scale = sample_cells / float(n)
-    return {"value": its_sample * scale, "unit": "iterations/s", "cores": cores, "kind": kind,
+    try:
+        with open("/proc/cpuinfo") as fh:
+            cpu_model = [ln.split(":", 1)[1].strip() for ln in fh if ln.startswith("model name")][0]
+    except Exception:
+        cpu_model = "unknown"
+    return {"value": its_sample * scale, "unit": "iterations/s", "cores": cores, "kind": kind, "cpu_model": cpu_model,
             "sample": f"{m} genes x {sample_cells} cells of the same synthetic matrix ({A.nnz} non-zeros), one c_nmf iteration "
                       f"= {per_iter:.3f} s on {cores} threads; value = sample it/s x {scale:.4g} (time per iteration is "
                       f"proportional to the cell count)",

@@ -25,3 +25,25 @@ np.savez_compressed(out, seed=seed, k=k, w_seed=w_seed, maxit=maxit, nmf_w=a["w"
                     ard_test_mse=b["test_mse"], ard_iter=b["iter"], ard_h=b["h"], proj_h=p["h"], proj_d=p["d"],
                     mask_bits=np.packbits(mask))
 print(out, os.path.getsize(out))
+
+# ---- pbmc3k goldens (BASELINE configs[0] and one fit of configs[1]) from the reference-compiled code ----
+from singlet_b200.datasets import get_pbmc3k_data, log_normalize  # noqa: E402
+from singlet_b200.rrng import RRng  # noqa: E402
+
+Ap = log_normalize(get_pbmc3k_data())
+Atp = Ap.T.tocsc()
+Atp.sort_indices()
+w10 = RRng(123).matrix_runif(10, Ap.shape[0])  # set.seed(123); matrix(runif(m * 10), 10, m)
+c1 = ref.nmf(Ap, Atp, w10, tol=1e-4, maxit=100, L1=(0.01, 0.01))
+port = Oracle("port").nmf(Ap, Atp, w10, tol=1e-4, maxit=100, L1=(0.01, 0.01))  # the port reports iterations / tol trace
+assert np.array_equal(port["w"], c1["w"]) and np.array_equal(port["h"], c1["h"])
+r = RRng(123)
+w_init = [r.matrix_runif(30, Ap.shape[0]) for _ in range(3)]  # cross_validate_nmf(ranks = 2:30, n_replicates = 3)
+seeds = [abs(r.dot_random_seed(3 + rep)) for rep in (1, 2, 3)]
+cv = ref.ard_nmf(Ap, Atp, w_init[0][:5, :], seeds[0], 20, tol=1e-4, maxit=100, L1=0.01, L2=0.0, overfit_threshold=1e-4,
+                 trace_test_mse=5)
+out2 = os.path.join(ROOT, "tests", "golden", "ref_pbmc3k.npz")
+np.savez_compressed(out2, c1_w=c1["w"].astype(np.float32), c1_h=c1["h"].astype(np.float32), c1_d=c1["d"], c1_iter=port["iter"],
+                    c1_tol=port["tol"], cv_seeds=np.array(seeds, dtype=np.uint64), cv_k=5, cv_test_mse=cv["test_mse"],
+                    cv_iter=cv["iter"], cv_tol=cv["tol"], cv_d=cv["d"])
+print(out2, os.path.getsize(out2), "C1 iterations", port["iter"], "CV trace", cv["test_mse"])

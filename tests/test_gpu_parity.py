@@ -406,3 +406,65 @@ def test_invalid_matrix_and_interrupt(handle):
     rc = handle.lib.sgl_nmf(handle.ptr, a, na, at, nat, 0.0, 50, 0.01, 0.01, 0.0, 0.0, 3, w.ctypes.data, d.ctypes.data, h.ctypes.data,
                             None, None, C.addressof(cb))
     assert rc == _lib.SGL_EINTERRUPT and [s[0] for s in seen] == [1, 2, 3] and polls[0] >= 3
+
+
+def test_pbmc3k_against_reference_goldens(handle, oracle):
+    """BASELINE configs[0] and one fit of configs[1] on the real dataset, against goldens produced by the reference's
+    own code (tests/golden/ref_pbmc3k.npz): same iteration count at tol = 1e-4, factors >= 0.999, test MSE within 1e-4."""
+    import os
+
+    from singlet_b200 import api
+    from singlet_b200.datasets import get_pbmc3k_data, log_normalize
+    from singlet_b200.rrng import RRng
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pbmc3k.npz"))
+    A = log_normalize(get_pbmc3k_data())
+    At = A.T.tocsc()
+    At.sort_indices()
+    w10 = RRng(123).matrix_runif(10, A.shape[0])
+    dev = api.c_nmf(A, At, 1e-4, 100, False, 0.01, 0.01, 0.0, 0.0, 0, w10)
+    assert dev["iter"] == int(z["c1_iter"])
+    perm = match_factors(z["c1_w"].astype(np.float64), dev["w"])
+    assert min_factor_cor(z["c1_w"].astype(np.float64), dev["w"], perm) >= COR_MIN
+    assert min_factor_cor(z["c1_h"].astype(np.float64), dev["h"], perm) >= COR_MIN
+    assert np.allclose(dev["d"][perm], z["c1_d"], rtol=5e-3)
+    tr_dev = oracle.mse_train(A, dev["w"], dev["d"], dev["h"])
+    tr_ref = oracle.mse_train(A, z["c1_w"].astype(np.float64), z["c1_d"], z["c1_h"].astype(np.float64))
+    assert abs(tr_dev - tr_ref) <= MSE_RTOL * tr_ref
+    r = RRng(123)
+    w_init = [r.matrix_runif(30, A.shape[0]) for _ in range(3)]
+    cv = api.c_ard_nmf(A, At, 1e-4, 100, False, 0.01, 0.0, 0, w_init[0][:5, :], int(z["cv_seeds"][0]), 20, 1e-4, 5)
+    assert list(cv["iter"]) == list(z["cv_iter"]) and np.allclose(cv["test_mse"], z["cv_test_mse"], rtol=MSE_RTOL)
+
+
+def test_device_train_and_test_mse(oracle):
+    """The fused MSE kernel: held-out (test, src/singlet.cpp:536-568) and not-held-out (train, harness-defined) means."""
+    from singlet_b200 import synth
+    from singlet_b200.sharded import CudaBackend
+
+    m, n, k = 500, 340, 7
+    A, At = _mk(m, n, 0.1, seed=15)
+    rs = np.random.RandomState(2)
+    w, h, d = rs.rand(k, m), rs.rand(k, n), rs.rand(k) + 0.5
+    be = CudaBackend(0)
+    try:
+        hA = be.upload(A)
+        mask = be.mask_build(hA, 123, 20, 0, 0, 0)
+        W, H = be.zeros_factor(m, k), be.zeros_factor(n, k)
+        be.factor_from_host(w, W)
+        be.factor_from_host(h, H)
+        import torch
+
+        dd = torch.ones(be.kp(k), dtype=torch.float64, device=be.device)
+        dd[:k] = torch.from_numpy(d).to(be.device)
+        out = be.zeros_f64(1)
+        be.mse(hA, mask, W, dd, H, k, 0, out)
+        assert abs(float(out[0]) / n - oracle.mse_test(A, w, d, h, 123, 20)) <= 1e-5 * oracle.mse_test(A, w, d, h, 123, 20)
+        be.mse(hA, mask, W, dd, H, k, 1, out)
+        ref = oracle.mse_train(A, w, d, h, 123, 20)
+        assert abs(float(out[0]) / n - ref) <= 1e-5 * ref
+        be.mse(hA, None, W, dd, H, k, 1, out)  # no mask: all m entries of every column
+        ref = oracle.mse_train(A, w, d, h)
+        assert abs(float(out[0]) / n - ref) <= 1e-5 * ref
+    finally:
+        be.close()

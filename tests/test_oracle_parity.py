@@ -171,3 +171,27 @@ def test_dense_variants_port_equals_reference(oracle, ref_oracle):
     a = oracle.ard_nmf_dense(D, D.T.copy(), w0, 123, 5, maxit=6, trace_test_mse=2, overfit_threshold=10.0)
     b = ref_oracle.ard_nmf_dense(D, D.T.copy(), w0, 123, 5, maxit=6, trace_test_mse=2, overfit_threshold=10.0)
     assert np.array_equal(a["test_mse"], b["test_mse"]) and np.array_equal(a["iter"], b["iter"]) and np.array_equal(a["h"], b["h"])
+
+
+def test_pbmc3k_goldens_from_reference_build(oracle):
+    """BASELINE configs[0] (`set.seed(123); run_nmf(A, rank = 10)` on log-normalised pbmc3k) and the first k = 5 fit
+    of configs[1], as produced by the reference's own code (oracle/_ref, scripts/make_goldens.py)."""
+    from singlet_b200.datasets import get_pbmc3k_data, log_normalize
+    from singlet_b200.rrng import RRng
+
+    z = np.load(os.path.join(GOLD, "ref_pbmc3k.npz"))
+    A = log_normalize(get_pbmc3k_data())
+    At = A.T.tocsc()
+    At.sort_indices()
+    w10 = RRng(123).matrix_runif(10, A.shape[0])
+    c1 = oracle.nmf(A, At, w10, tol=1e-4, maxit=100, L1=(0.01, 0.01))
+    assert c1["iter"] == int(z["c1_iter"]) == 24 and np.array_equal(c1["d"], z["c1_d"]) and np.array_equal(c1["tol"], z["c1_tol"])
+    assert np.array_equal(c1["w"].astype(np.float32), z["c1_w"]) and np.array_equal(c1["h"].astype(np.float32), z["c1_h"])
+    r = RRng(123)
+    w_init = [r.matrix_runif(30, A.shape[0]) for _ in range(3)]
+    seeds = [abs(r.dot_random_seed(3 + rep)) for rep in (1, 2, 3)]
+    assert [int(s) for s in z["cv_seeds"]] == seeds
+    cv = oracle.ard_nmf(A, At, w_init[0][:5, :], seeds[0], 20, tol=1e-4, maxit=100, L1=0.01, L2=0.0, overfit_threshold=1e-4,
+                        trace_test_mse=5)
+    assert np.array_equal(cv["test_mse"], z["cv_test_mse"]) and np.array_equal(cv["iter"], z["cv_iter"])
+    assert np.array_equal(cv["d"], z["cv_d"])
