@@ -100,11 +100,13 @@ struct sgl_handle {
     DevBuf<int64_t> counts;
     DevBuf<unsigned long long> workctr;
     double* pinned = nullptr;  // 64 doubles of pinned host scratch
-    // pinned staging ring for uploads: host threads pack {int32 row, float value} records into it
-    static constexpr int NSTAGE = 3;
-    uint2* stage[NSTAGE] = {nullptr, nullptr, nullptr};
-    cudaEvent_t stage_ev[NSTAGE] = {nullptr, nullptr, nullptr};
-    size_t stage_records = 0;
+    // upload workers: every host thread owns two pinned staging buffers, a stream and two events
+    static constexpr int MAX_WORKERS = 32;
+    static constexpr size_t STAGE_RECORDS = (size_t)1 << 19;  // 512k records = 4 MB per buffer
+    uint2* stage[MAX_WORKERS][2] = {};
+    cudaEvent_t stage_ev[MAX_WORKERS][2] = {};
+    cudaStream_t stage_stream[MAX_WORKERS] = {};
+    int n_workers = 0;
     // optional per-kernel-kind event timing (bench.py's roofline numbers are measured live with it)
     bool profiling = false;
     struct Span { int kind; cudaEvent_t a, b; int64_t bytes; };
@@ -249,20 +251,24 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
         matrix_release(m);
         return fail(SGL_ENOMEM, "matrix upload: cudaMalloc failed for %lld non-zeros", (long long)nnz);
     }
-    // Records are packed on the host: several threads convert the dgCMatrix slots (int32 i, double x)
-    // of a piece into {int32 row, float value} records inside a pinned staging buffer, which is then
-    // copied straight into m->rec while the threads fill the next buffer (3-deep ring). This moves
-    // 8 B per non-zero over PCIe instead of 12 B and keeps the copy engine busy.
-    const size_t PIECE = (size_t)8 << 20;  // records per staging buffer (64 MB)
-    if (!h->stage[0]) {
-        for (int q = 0; q < sgl_handle::NSTAGE; ++q) {
-            if (cudaMallocHost(&h->stage[q], PIECE * sizeof(uint2)) != cudaSuccess ||
-                cudaEventCreateWithFlags(&h->stage_ev[q], cudaEventDisableTiming) != cudaSuccess) {
-                matrix_release(m);
-                return fail(SGL_ENOMEM, "matrix upload: pinned staging allocation failed");
-            }
+    // Records are packed on the host: every worker thread converts pieces of the dgCMatrix slots (int32 i,
+    // double x) into {int32 row, float value} records inside its own pinned staging buffers and copies them
+    // straight into m->rec on its own stream, double-buffered, so packing and PCIe traffic overlap across and
+    // within workers. 8 B per non-zero cross PCIe instead of 12 B.
+    unsigned hw = std::thread::hardware_concurrency();
+    int n_threads = (int)(hw == 0 ? 4 : (hw > (unsigned)sgl_handle::MAX_WORKERS ? (unsigned)sgl_handle::MAX_WORKERS : hw));
+    if (const char* ev = getenv("SGL_UPLOAD_THREADS")) n_threads = atoi(ev) > 0 ? atoi(ev) : n_threads;
+    if (n_threads > sgl_handle::MAX_WORKERS) n_threads = sgl_handle::MAX_WORKERS;
+    for (int q = h->n_workers; q < n_threads; ++q) {
+        bool ok = cudaStreamCreateWithFlags(&h->stage_stream[q], cudaStreamNonBlocking) == cudaSuccess;
+        for (int bb = 0; bb < 2 && ok; ++bb)
+            ok = cudaMallocHost(&h->stage[q][bb], sgl_handle::STAGE_RECORDS * sizeof(uint2)) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&h->stage_ev[q][bb], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            matrix_release(m);
+            return fail(SGL_ENOMEM, "matrix upload: pinned staging allocation failed");
         }
-        h->stage_records = PIECE;
+        h->n_workers = q + 1;
     }
     int32_t* d_p = nullptr;
     int64_t max_cols = 0;
@@ -271,11 +277,8 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
         matrix_release(m);
         return fail(SGL_ENOMEM, "matrix upload: staging cudaMalloc failed");
     }
-    unsigned hw = std::thread::hardware_concurrency();
-    const int n_threads = (int)(hw == 0 ? 4 : (hw > 12 ? 12 : hw));
     int rc = SGL_OK;
     int64_t col_off = 0, nnz_off = 0;
-    int64_t piece_no = 0;
     for (int q = 0; q < n_chunks && rc == SGL_OK; ++q) {
         const sgl_csc& c = chunks[q];
         const int64_t cn = c.p[c.ncol];
@@ -284,37 +287,44 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
         colptr_from_p32_kernel<<<blocks_for(c.ncol + 1, 256), 256, 0, h->stream>>>(d_p, c.ncol, nnz_off, m->colptr + col_off, last);
         ++h->launches;
         cudaStreamSynchronize(h->stream);  // d_p is reused by the next chunk
-        for (int64_t o = 0; o < cn; o += (int64_t)PIECE, ++piece_no) {
-            const int64_t len = (cn - o) < (int64_t)PIECE ? (cn - o) : (int64_t)PIECE;
-            const int sidx = (int)(piece_no % sgl_handle::NSTAGE);
-            if (piece_no >= sgl_handle::NSTAGE) cudaEventSynchronize(h->stage_ev[sidx]);  // buffer free again
-            uint2* dstbuf = h->stage[sidx];
-            const int32_t* si = c.i + o;
-            const double* sx = c.x + o;
-            auto work = [dstbuf, si, sx](int64_t b, int64_t e) {
-                for (int64_t t = b; t < e; ++t) {
+        const int64_t PIECE = (int64_t)sgl_handle::STAGE_RECORDS;
+        const int64_t n_pieces = (cn + PIECE - 1) / PIECE;
+        const int nt = (int)(n_pieces < n_threads ? (n_pieces > 0 ? n_pieces : 1) : n_threads);
+        std::vector<int> worker_rc((size_t)nt, 0);
+        uint2* dst_dev = m->rec + nnz_off;
+        const int device = h->device;
+        auto worker = [&, dst_dev, device](int wid) {
+            if (cudaSetDevice(device) != cudaSuccess) { worker_rc[(size_t)wid] = 1; return; }
+            int use = 0;
+            int64_t done_pieces = 0;
+            for (int64_t pc = wid; pc < n_pieces; pc += nt, ++done_pieces, use ^= 1) {
+                const int64_t o = pc * PIECE;
+                const int64_t len = (cn - o) < PIECE ? (cn - o) : PIECE;
+                if (done_pieces >= 2) cudaEventSynchronize(h->stage_ev[wid][use]);  // buffer free again
+                uint2* buf = h->stage[wid][use];
+                const int32_t* si = c.i + o;
+                const double* sx = c.x + o;
+                for (int64_t t = 0; t < len; ++t) {
                     const float v = (float)sx[t];
                     uint32_t bits;
                     std::memcpy(&bits, &v, 4);
-                    dstbuf[t] = make_uint2((uint32_t)si[t], bits);
+                    buf[t] = make_uint2((uint32_t)si[t], bits);
                 }
-            };
-            const int nt = len < (1 << 16) ? 1 : n_threads;
-            if (nt == 1) {
-                work(0, len);
-            } else {
-                std::vector<std::thread> pool;
-                const int64_t per = (len + nt - 1) / nt;
-                for (int w = 0; w < nt; ++w) {
-                    const int64_t b = w * per, e = (b + per) < len ? (b + per) : len;
-                    if (b < e) pool.emplace_back(work, b, e);
-                }
-                for (auto& th : pool) th.join();
+                if (cudaMemcpyAsync(dst_dev + o, buf, sizeof(uint2) * (size_t)len, cudaMemcpyHostToDevice, h->stage_stream[wid]) != cudaSuccess)
+                    worker_rc[(size_t)wid] = 1;
+                cudaEventRecord(h->stage_ev[wid][use], h->stage_stream[wid]);
             }
-            cudaMemcpyAsync(m->rec + nnz_off + o, dstbuf, sizeof(uint2) * (size_t)len, cudaMemcpyHostToDevice, h->stream);
-            cudaEventRecord(h->stage_ev[sidx], h->stream);
+            if (cudaStreamSynchronize(h->stage_stream[wid]) != cudaSuccess) worker_rc[(size_t)wid] = 1;
+        };
+        if (nt <= 1) {
+            worker(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int wq = 0; wq < nt; ++wq) pool.emplace_back(worker, wq);
+            for (auto& th : pool) th.join();
         }
-        if (cudaGetLastError() != cudaSuccess) rc = fail(SGL_ECUDA, "matrix upload: copy failed");
+        for (int wq = 0; wq < nt; ++wq)
+            if (worker_rc[(size_t)wq]) rc = fail(SGL_ECUDA, "matrix upload: copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
         col_off += c.ncol;
         nnz_off += cn;
     }
@@ -976,9 +986,12 @@ int sgl_destroy(sgl_handle* h) {
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
-    for (int q = 0; q < sgl_handle::NSTAGE; ++q) {
-        if (h->stage[q]) cudaFreeHost(h->stage[q]);
-        if (h->stage_ev[q]) cudaEventDestroy(h->stage_ev[q]);
+    for (int q = 0; q < h->n_workers; ++q) {
+        for (int b = 0; b < 2; ++b) {
+            if (h->stage[q][b]) cudaFreeHost(h->stage[q][b]);
+            if (h->stage_ev[q][b]) cudaEventDestroy(h->stage_ev[q][b]);
+        }
+        if (h->stage_stream[q]) cudaStreamDestroy(h->stage_stream[q]);
     }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
