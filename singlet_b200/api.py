@@ -18,6 +18,7 @@ import math
 import sys
 
 import numpy as np
+import pandas as pd
 
 from . import _lib
 from .rrng import RRng
@@ -383,8 +384,6 @@ def cross_validate_nmf(A, ranks, n_replicates=3, tol=1e-4, maxit=100, verbose=1,
                        test_density=0.05, tol_overfit=1e-4, trace_test_mse=5, rng=None, handle: Handle | None = None):
     """``cross_validate_nmf`` (reference R/cross_validate_nmf.R:18-105). Returns a pandas DataFrame with
     columns ``k, rep, test_error, iter, tol`` (one row per traced iteration of every fit)."""
-    import pandas as pd
-
     if L1 >= 1:
         raise ValueError("L1 penalty must be strictly in the range (0, 1]")
     r = _rng(rng)
@@ -450,8 +449,6 @@ def ard_nmf(A, k_init=2, k_max=100, k_min=2, n_replicates=1, tol=1e-5, cv_tol=1e
             handle: Handle | None = None):
     """``ard_nmf`` (reference R/ard_nmf.R:31-193): rank search by cross-validated fits, then a final
     unmasked fit at the best rank. Returns the sorted model plus ``cv_data`` (DataFrame)."""
-    import pandas as pd
-
     if not L1 < 1:
         raise ValueError("L1 penalty must be strictly in the range (0, 1]")
     if k_init is None or k_init < k_min:

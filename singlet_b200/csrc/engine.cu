@@ -85,6 +85,7 @@ struct sgl_mask {
     std::map<int, uint2*> stream_train;  // its warp streams, per padded rank (lazily built)
     int64_t* mptr = nullptr;     // ncol + 1
     uint2* mrec = nullptr;       // held-out {row, value bits}
+    int64_t mrec_cap = 0;        // records allocated (a re-seeded mask reuses the buffers)
     int64_t n_masked = 0, n_masked_nz = 0;
 };
 
@@ -98,7 +99,11 @@ struct sgl_handle {
     DevBuf<float> bparts, blink, gram_f, gram_f_nojit, inv_diag;
     DevBuf<double> part, scal, losses, gram_w;
     DevBuf<int64_t> counts;
-    DevBuf<unsigned long long> workctr;
+    DevBuf<unsigned long long> workctr, held;
+    // factor buffers of the fit in flight and the FP64 staging of factor up/downloads: kept across calls so
+    // that the 87 fits of a CV sweep do not pay cudaMalloc / cudaFree (a device-wide sync) per fit
+    DevBuf<float> fitW, fitH, fitWprev;
+    DevBuf<double> fit_small, ftmp;
     double* pinned = nullptr;  // 64 doubles of pinned host scratch
     // upload workers: every host thread owns two pinned staging buffers, a stream and two events
     static constexpr int MAX_WORKERS = 32;
@@ -356,15 +361,23 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
 }
 
 // re-lay `rec` (column-compressed, same structure as m->rec) out as warp streams for tile index ti
-static int build_stream(sgl_handle* h, const sgl_matrix* m, const TileIndex& ti, const uint2* rec, uint2** out) {
-    uint2* st = nullptr;
-    // one CHUNK of slack: the kernel's last cp.async chunk of a stream may start inside the array only
-    SGL_CUDA(cudaMalloc(&st, sizeof(uint2) * (size_t)(ti.stream_len + 64)));
+static int fill_stream(sgl_handle* h, const sgl_matrix* m, const TileIndex& ti, const uint2* rec, uint2* st) {
     const int64_t warps = ti.n_groups * ti.n_tiles;
     if (warps > 0) {
         stream_fill_kernel<<<blocks_for(warps, 8), 256, 0, h->stream>>>(rec, m->colptr, ti.tileptr, ti.goff, m->ncol, ti.ncol_pad,
                                                                      ti.n_tiles, ti.rb_rows, ti.nc, ti.pad, ti.n_groups, st);
         LAUNCH_CHECK(h);
+    }
+    return SGL_OK;
+}
+static int build_stream(sgl_handle* h, const sgl_matrix* m, const TileIndex& ti, const uint2* rec, uint2** out) {
+    uint2* st = nullptr;
+    // one CHUNK of slack: the kernel's last cp.async chunk of a stream may start inside the array only
+    SGL_CUDA(cudaMalloc(&st, sizeof(uint2) * (size_t)(ti.stream_len + 64)));
+    const int rc = fill_stream(h, m, ti, rec, st);
+    if (rc != SGL_OK) {
+        cudaFree(st);
+        return rc;
     }
     *out = st;
     return SGL_OK;
@@ -612,7 +625,32 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
         }
         LAUNCH_CHECK(h);
     } else {
-        if (KPV <= 64) {
+        if (KPV <= 32) {
+            // sub-warp solver: G columns per warp; the whole CTA shares one column group (WS = 4) when the
+            // one-group-per-warp grid would leave most SMs without work
+            int G = 1;
+            DISPATCH_KP(KPV, G = (KP <= 32) ? MaskedSubCfg<(KP <= 32 ? KP : 32)>::G : 1);
+            const int64_t ctas1 = (ncol + 4 * G - 1) / (4 * G);
+            const bool share = ctas1 < 2 * (int64_t)h->sm_count;
+            n_parts = share ? (ncol + G - 1) / G : ctas1;
+            SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
+            switch (KPV) {
+#define MASKED_SUB_CASE(KPC)                                                                                        \
+    case KPC:                                                                                                       \
+        if (share)                                                                                                  \
+            nnls_masked_sub_kernel<KPC, 4><<<(unsigned)n_parts, 128, 0, h->stream>>>(                                \
+                Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, mask->mptr, mask->mrec, ncol, k, (float)L1, \
+                (float)L2, h->part.p);                                                                              \
+        else                                                                                                        \
+            nnls_masked_sub_kernel<KPC, 1><<<(unsigned)n_parts, 128, 0, h->stream>>>(                                \
+                Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, mask->mptr, mask->mrec, ncol, k, (float)L1, \
+                (float)L2, h->part.p);                                                                              \
+        break;
+                MASKED_SUB_CASE(4) MASKED_SUB_CASE(8) MASKED_SUB_CASE(16) MASKED_SUB_CASE(32)
+                default: break;
+#undef MASKED_SUB_CASE
+            }
+        } else if (KPV <= 64) {
             const int warps = 4;
             n_parts = (ncol + warps - 1) / warps;
             SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
@@ -696,11 +734,17 @@ static int scan_counts(sgl_handle* h, const int64_t* counts, int64_t n, int64_t*
     return SGL_OK;
 }
 
+// Builds the held-out lists and the training copy of X for (seed, inv_density). `reuse` (optional) is a mask of the
+// same matrix and orientation whose device buffers are refilled in place -- a CV sweep changes the seed once per
+// replicate, and freeing / re-allocating ~100 MB of lists and streams costs far more than refilling them.
 static int mask_build(sgl_handle* h, const sgl_matrix* X, uint64_t seed, uint64_t inv_density, int mask_t,
-                      int64_t col_offset, int64_t row_offset, sgl_mask** out) {
-    if (inv_density == 0) return fail(SGL_EINVAL, "inv_density must be >= 1");
+                      int64_t col_offset, int64_t row_offset, sgl_mask** out, sgl_mask* reuse = nullptr) {
+    if (inv_density == 0) {
+        if (reuse) mask_release(reuse);
+        return fail(SGL_EINVAL, "inv_density must be >= 1");
+    }
     SGL_TRY(set_device(h));
-    sgl_mask* m = new sgl_mask();
+    sgl_mask* m = reuse ? reuse : new sgl_mask();
     m->X = X;
     m->seed = seed;
     m->inv_density = inv_density;
@@ -714,16 +758,15 @@ static int mask_build(sgl_handle* h, const sgl_matrix* X, uint64_t seed, uint64_
     gen.col_offset = col_offset;
     gen.row_offset = row_offset;
     int rc = SGL_OK;
-    unsigned long long* d_held = nullptr;
     do {
         if ((rc = h->counts.ensure((size_t)X->ncol + 2)) != SGL_OK) break;
-        if (cudaMalloc(&m->mptr, sizeof(int64_t) * (size_t)(X->ncol + 1)) != cudaSuccess ||
-            cudaMalloc(&m->rec_train, sizeof(uint2) * (size_t)(X->nnz > 0 ? X->nnz : 1)) != cudaSuccess ||
-            cudaMalloc(&d_held, sizeof(unsigned long long)) != cudaSuccess) {
+        if ((rc = h->held.ensure(1)) != SGL_OK) break;
+        if ((!m->mptr && cudaMalloc(&m->mptr, sizeof(int64_t) * (size_t)(X->ncol + 1)) != cudaSuccess) ||
+            (!m->rec_train && cudaMalloc(&m->rec_train, sizeof(uint2) * (size_t)(X->nnz > 0 ? X->nnz : 1)) != cudaSuccess)) {
             rc = fail(SGL_ENOMEM, "mask build: cudaMalloc failed");
             break;
         }
-        cudaMemsetAsync(d_held, 0, sizeof(unsigned long long), h->stream);
+        cudaMemsetAsync(h->held.p, 0, sizeof(unsigned long long), h->stream);
         const unsigned grid = blocks_for(X->ncol, 8);
         if (X->ncol > 0) {
             mask_lists_kernel<0><<<grid, 256, 0, h->stream>>>(gen, X->ncol, X->nrow, X->colptr, X->rec, h->counts.p, nullptr, nullptr);
@@ -738,25 +781,37 @@ static int mask_build(sgl_handle* h, const sgl_matrix* X, uint64_t seed, uint64_
             break;
         }
         m->n_masked = total;
-        if (cudaMalloc(&m->mrec, sizeof(uint2) * (size_t)(total > 0 ? total : 1)) != cudaSuccess) {
-            rc = fail(SGL_ENOMEM, "mask build: cudaMalloc(%lld records) failed", (long long)total);
-            break;
+        if (!m->mrec || total > m->mrec_cap) {
+            if (m->mrec) cudaFree(m->mrec);
+            m->mrec = nullptr;
+            m->mrec_cap = total + total / 32 + 1024;  // slack: another seed holds out a slightly different number
+            if (cudaMalloc(&m->mrec, sizeof(uint2) * (size_t)m->mrec_cap) != cudaSuccess) {
+                m->mrec_cap = 0;
+                rc = fail(SGL_ENOMEM, "mask build: cudaMalloc(%lld records) failed", (long long)total);
+                break;
+            }
         }
         if (X->ncol > 0) {
             mask_lists_kernel<1><<<grid, 256, 0, h->stream>>>(gen, X->ncol, X->nrow, X->colptr, X->rec, nullptr, m->mptr, m->mrec);
             ++h->launches;
-            mask_records_kernel<<<grid, 256, 0, h->stream>>>(gen, X->ncol, X->colptr, X->rec, m->rec_train, d_held);
+            mask_records_kernel<<<grid, 256, 0, h->stream>>>(gen, X->ncol, X->colptr, X->rec, m->rec_train, h->held.p);
             ++h->launches;
         }
         unsigned long long held = 0;
-        cudaMemcpyAsync(&held, d_held, sizeof(held), cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(&held, h->held.p, sizeof(held), cudaMemcpyDeviceToHost, h->stream);
+        // the training streams already laid out for some padded ranks are refilled from the new training copy
+        for (auto& kv : m->stream_train) {
+            auto it = X->tiles.find(kv.first);
+            if (it == X->tiles.end() || !kv.second) { rc = fail(SGL_EINVAL, "mask build: stale training stream"); break; }
+            if ((rc = fill_stream(h, X, it->second, m->rec_train, kv.second)) != SGL_OK) break;
+        }
+        if (rc != SGL_OK) break;
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
             rc = fail(SGL_ECUDA, "mask build: fill pass failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
         m->n_masked_nz = (int64_t)held;
     } while (0);
-    if (d_held) cudaFree(d_held);
     if (rc != SGL_OK) {
         mask_release(m);
         return rc;
@@ -790,13 +845,12 @@ static int factor_upload(sgl_handle* h, const double* host, int k, int64_t cols,
     const int KPV = kp_of(k);
     const size_t n = (size_t)k * (size_t)cols;
     if (n == 0) return SGL_OK;
-    double* tmp = nullptr;
-    SGL_CUDA(cudaMalloc(&tmp, sizeof(double) * n));
+    SGL_TRY(h->ftmp.ensure(n));
+    double* tmp = h->ftmp.p;
     cudaMemcpyAsync(tmp, host, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream);
     factor_to_dev_kernel<<<blocks_for(cols * KPV, 256), 256, 0, h->stream>>>(tmp, k, KPV, cols, dev);
     ++h->launches;
     cudaError_t e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
     if (e != cudaSuccess) return fail(SGL_ECUDA, "factor upload: %s", cudaGetErrorString(e));
     return SGL_OK;
 }
@@ -804,13 +858,12 @@ static int factor_download(sgl_handle* h, const float* dev, int k, int64_t cols,
     const int KPV = kp_of(k);
     const size_t n = (size_t)k * (size_t)cols;
     if (n == 0) return SGL_OK;
-    double* tmp = nullptr;
-    SGL_CUDA(cudaMalloc(&tmp, sizeof(double) * n));
+    SGL_TRY(h->ftmp.ensure(n));
+    double* tmp = h->ftmp.p;
     factor_to_host_kernel<<<blocks_for((int64_t)n, 256), 256, 0, h->stream>>>(dev, k, KPV, cols, tmp);
     ++h->launches;
     cudaMemcpyAsync(host, tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
     cudaError_t e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
     if (e != cudaSuccess) return fail(SGL_ECUDA, "factor download: %s", cudaGetErrorString(e));
     return SGL_OK;
 }
@@ -846,31 +899,33 @@ static int cached_mask(sgl_handle* h, const sgl_matrix* X, uint64_t seed, uint64
         *out = *slot;
         return SGL_OK;
     }
-    if (*slot) {
+    // same matrix and orientation, other seed / density: refill the buffers in place
+    sgl_mask* reuse = nullptr;
+    if (*slot && (*slot)->X == X && (*slot)->mask_t == mask_t && (*slot)->col_offset == 0 && (*slot)->row_offset == 0) {
+        reuse = *slot;
+    } else if (*slot) {
         mask_release(*slot);
-        *slot = nullptr;
     }
-    SGL_TRY(mask_build(h, X, seed, inv, mask_t, 0, 0, slot));
+    *slot = nullptr;  // mask_build releases `reuse` itself when it fails
+    SGL_TRY(mask_build(h, X, seed, inv, mask_t, 0, 0, slot, reuse));
     *out = *slot;
     return SGL_OK;
 }
 
-struct FitBuffers {  // device state of one fit
+struct FitBuffers {  // device state of one fit: views into the handle's grow-only buffers (one fit per handle at a time)
     float *W = nullptr, *H = nullptr, *Wprev = nullptr;
     double *gram = nullptr, *dvec = nullptr, *sums = nullptr;
-    ~FitBuffers() {
-        if (W) cudaFree(W);
-        if (H) cudaFree(H);
-        if (Wprev) cudaFree(Wprev);
-        if (gram) cudaFree(gram);
-        if (dvec) cudaFree(dvec);
-        if (sums) cudaFree(sums);
-    }
-    int alloc(int KPV, int64_t m, int64_t n) {
-        if (cudaMalloc(&W, sizeof(float) * (size_t)m * KPV) != cudaSuccess || cudaMalloc(&H, sizeof(float) * (size_t)(n > 0 ? n : 1) * KPV) != cudaSuccess ||
-            cudaMalloc(&Wprev, sizeof(float) * (size_t)m * KPV) != cudaSuccess || cudaMalloc(&gram, sizeof(double) * KPV * KPV) != cudaSuccess ||
-            cudaMalloc(&dvec, sizeof(double) * KPV) != cudaSuccess || cudaMalloc(&sums, sizeof(double) * 8) != cudaSuccess)
-            return fail(SGL_ENOMEM, "fit: cudaMalloc of factor buffers failed (m=%lld n=%lld KP=%d)", (long long)m, (long long)n, KPV);
+    int alloc(sgl_handle* h, int KPV, int64_t m, int64_t n) {
+        SGL_TRY(h->fitW.ensure((size_t)m * KPV));
+        SGL_TRY(h->fitH.ensure((size_t)(n > 0 ? n : 1) * KPV));
+        SGL_TRY(h->fitWprev.ensure((size_t)m * KPV));
+        SGL_TRY(h->fit_small.ensure((size_t)KPV * KPV + KPV + 8));
+        W = h->fitW.p;
+        H = h->fitH.p;
+        Wprev = h->fitWprev.p;
+        gram = h->fit_small.p;
+        dvec = gram + (size_t)KPV * KPV;
+        sums = dvec + KPV;
         return SGL_OK;
     }
 };
@@ -916,7 +971,7 @@ static int fit_outputs(sgl_handle* h, FitBuffers& fb, int k, int64_t m, int64_t 
 
 static int fit_init(sgl_handle* h, FitBuffers& fb, int k, int64_t m, int64_t n, const double* w) {
     const int KPV = kp_of(k);
-    SGL_TRY(fb.alloc(KPV, m, n));
+    SGL_TRY(fb.alloc(h, KPV, m, n));
     SGL_TRY(factor_upload(h, w, k, m, fb.W));
     SGL_CUDA(cudaMemsetAsync(fb.H, 0, sizeof(float) * (size_t)(n > 0 ? n : 1) * KPV, h->stream));  // h = 0 (:640)
     std::vector<double> ones((size_t)KPV, 1.0);                                                   // d = 1 (:641)
@@ -982,7 +1037,8 @@ int sgl_destroy(sgl_handle* h) {
     matrix_release(h->cA);
     matrix_release(h->cAt);
     h->bparts.release(); h->blink.release(); h->gram_f.release(); h->gram_f_nojit.release(); h->inv_diag.release();
-    h->part.release(); h->scal.release(); h->losses.release(); h->gram_w.release(); h->counts.release(); h->workctr.release();
+    h->part.release(); h->scal.release(); h->losses.release(); h->gram_w.release(); h->counts.release(); h->workctr.release(); h->held.release();
+    h->fitW.release(); h->fitH.release(); h->fitWprev.release(); h->fit_small.release(); h->ftmp.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);

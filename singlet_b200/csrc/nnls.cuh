@@ -426,6 +426,311 @@ nnls_masked_kernel(const float* __restrict__ Bparts, int splits, float* __restri
     }
 }
 
+// Sub-warp variant for KP <= 32: L lanes cooperate on one column, each holding RPT = KP / L consecutive
+// rows of a_i in registers, so one warp solves G = 32 / L columns at once (L = 1 for KP <= 8: a whole
+// column per thread). A coordinate step then costs the same ~20 instructions per WARP as in the
+// warp-per-column kernel above but advances G columns, and every lane does useful FMAs in the
+// Gram-correction phase. When there are too few columns to fill the chip (the H update of a small
+// matrix: few cells, long held-out lists) WS = 4 warps share one column group: each accumulates the
+// correction over a quarter of the held-out rows and warp 0 folds the partial sums through shared
+// memory before solving.
+#ifndef SGL_MASKED32_MINB
+#define SGL_MASKED32_MINB 3
+#endif
+template <int KP>
+struct MaskedSubCfg {
+    static constexpr int L = (KP <= 8) ? 1 : KP / 4;  // lanes per column
+    static constexpr int RPT = KP / L;                // rows of a_i per lane (4 or 8)
+    static constexpr int G = 32 / L;                  // columns per warp
+    static constexpr int WARPS = 4;
+};
+
+template <int KP, int WS>
+__global__ void __launch_bounds__(MaskedSubCfg<KP>::WARPS * 32, SGL_MASKED32_MINB)
+nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __restrict__ X,
+                       const float* __restrict__ gram_f,   // [KP][KP] jitter-free FP32 Gram
+                       const float* __restrict__ F,        // gather factor [rows][KP]
+                       const int64_t* __restrict__ colptr, const int64_t* __restrict__ mptr,
+                       const uint2* __restrict__ mrec, int64_t ncol, int k, float L1, float L2,
+                       double* __restrict__ rowsum_part) {
+    using C = MaskedSubCfg<KP>;
+    constexpr int L = C::L, RPT = C::RPT, G = C::G, WARPS = C::WARPS;
+    constexpr int CG = WARPS / WS;  // column groups per CTA
+    static_assert(WS == 1 || WS == WARPS, "a column group is owned by one warp or by the whole CTA");
+    constexpr int D = (L == 1) ? 4 : 8;        // held-out rows in flight per column
+    constexpr int CPL = (L > 1) ? 1 : KP / 4;  // 16-byte chunks of a factor row copied by one lane
+    __shared__ double sred[WARPS][KP];
+    __shared__ float sacc[(WS > 1) ? RPT * KP * 32 : 1];
+    __shared__ __align__(16) float sring[WARPS][D][32 * CPL * 4];  // [warp][stage][column slot][KP]
+    __shared__ __align__(8) uint2 sidx[WARPS][2][G][D];            // held-out records of two blocks of D entries
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lig = lane % L;  // lane inside its column's group: owns rows lig*RPT .. lig*RPT+RPT-1
+    const int gi = lane / L;   // column slot inside the warp
+    const int cgi = warp / WS, wsub = warp % WS;
+    const int64_t col = ((int64_t)blockIdx.x * CG + cgi) * G + gi;
+    const bool in_range = col < ncol;
+    const bool solve = in_range && (colptr[col] != colptr[col + 1]);
+
+    // ---- correction G_M = sum over held-out rows of f f^T (reference :460-461), my RPT rows of it ----
+    float a[RPT][KP];
+#pragma unroll
+    for (int c = 0; c < RPT; ++c)
+#pragma unroll
+        for (int i = 0; i < KP; ++i) a[c][i] = 0.f;
+    int64_t mb = 0;
+    int my_n = 0;  // my share: held-out entries mb + wsub + WS * t, t < my_n
+    if (solve) {
+        mb = mptr[col];
+        const int64_t len = mptr[col + 1] - mb;
+        my_n = (int)((len - wsub + WS - 1) / WS);
+        if (my_n < 0) my_n = 0;
+    }
+    const int max_n = __reduce_max_sync(0xffffffffu, my_n);
+    // The loads of a held-out entry form a dependent index -> factor-row chain with L2 latency on both links, and
+    // loads into registers cannot be kept many entries deep (a warp has six scoreboards: waiting for an old load
+    // waits for the young ones too). So both links go through shared memory with cp.async (LDGSTS): the factor
+    // rows of D entries per column are in flight in a ring of D stages, and the records of block b + 2 (D entries)
+    // are copied while block b is consumed. One commit group per entry; out-of-range entries are zero-filled
+    // (they add nothing), so the consumer needs no predicates.
+    const uint32_t ring = smem_u32(&sring[warp][0][0]);
+    const uint32_t iring = smem_u32(&sidx[warp][0][0][0]);
+    constexpr uint32_t STAGE_BYTES = 32 * CPL * 16;
+    constexpr int IPL = (D + L - 1) / L;  // records copied per lane per block
+    auto copy_idx = [&](int blk) {  // records of entries blk*D .. blk*D+D-1 of my column -> sidx[blk & 1][gi][*]
+#pragma unroll
+        for (int q = 0; q < IPL; ++q) {
+            const int e = lig + q * L;
+            if (e < D) {
+                const int t = blk * D + e;
+                const bool ok = t < my_n;
+                cp_async8(iring + (uint32_t)((((blk & 1) * G + gi) * D + e) * 8), mrec + (ok ? mb + wsub + (int64_t)WS * t : 0), ok ? 8u : 0u);
+            }
+        }
+    };
+    auto issue = [&](int t, int stage) {  // my 16-byte chunk(s) of the factor row of my column's entry t
+        const uint32_t row = sidx[warp][(t / D) & 1][gi][t % D].x;
+        const bool ok = t < my_n;
+        const float* src = F + (int64_t)row * KP + (L > 1 ? lig * 4 : 0);
+#pragma unroll
+        for (int q = 0; q < CPL; ++q)
+            cp_async16(ring + (uint32_t)stage * STAGE_BYTES + (uint32_t)(lane * CPL + q) * 16u, src + 4 * q, ok ? 16u : 0u);
+    };
+    copy_idx(0);
+    copy_idx(1);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        issue(d, d);
+        cp_async_commit();
+    }
+    for (int tb = 0; tb < max_n; tb += D) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int t = tb + d;
+            if (t < max_n) {  // warp-uniform
+                cp_async_wait<D - 1>();  // entry t (and, at d == 0, the records of the next block) has landed
+                __syncwarp();
+                const float4* st4 = reinterpret_cast<const float4*>(&sring[warp][d][0]);
+                float f[KP], mine[RPT];
+#pragma unroll
+                for (int i4 = 0; i4 < KP / 4; ++i4) {
+                    const float4 v = st4[gi * (KP / 4) + i4];  // same address on the L lanes of a group: broadcast
+                    f[4 * i4 + 0] = v.x; f[4 * i4 + 1] = v.y; f[4 * i4 + 2] = v.z; f[4 * i4 + 3] = v.w;
+                }
+                if constexpr (L == 1) {
+#pragma unroll
+                    for (int c = 0; c < RPT; ++c) mine[c] = f[c];
+                } else {
+                    const float4 v = st4[lane];  // my RPT == 4 rows of f
+                    mine[0] = v.x; mine[1] = v.y; mine[2] = v.z; mine[3] = v.w;
+                }
+#pragma unroll
+                for (int c = 0; c < RPT; ++c)
+#pragma unroll
+                    for (int i = 0; i < KP; ++i) a[c][i] = fmaf(mine[c], f[i], a[c][i]);
+                __syncwarp();  // the stage (and, at d == 0, the record slot of block tb / D) is free again
+                issue(t + D, d);
+                if (d == 0) copy_idx(tb / D + 2);
+                cp_async_commit();
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if constexpr (WS > 1) {  // fold the WS partial corrections into warp 0, one warp at a time
+        for (int w = 1; w < WS; ++w) {
+            if (wsub == w) {
+#pragma unroll
+                for (int c = 0; c < RPT; ++c)
+#pragma unroll
+                    for (int i = 0; i < KP; ++i) sacc[(c * KP + i) * 32 + lane] = a[c][i];
+            }
+            __syncthreads();
+            if (wsub == 0) {
+#pragma unroll
+                for (int c = 0; c < RPT; ++c)
+#pragma unroll
+                    for (int i = 0; i < KP; ++i) a[c][i] += sacc[(c * KP + i) * 32 + lane];
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- right-hand side, warm start, a_i = G - G_M (the 1e-15 jitters cancel, App. A-11) ----
+    float b[RPT], x[RPT], inv[RPT];
+#pragma unroll
+    for (int c = 0; c < RPT; ++c) { b[c] = 0.f; x[c] = 0.f; inv[c] = 0.f; }
+    const bool owner_warp = (wsub == 0);
+    if (in_range && owner_warp) {
+#pragma unroll
+        for (int c4 = 0; c4 < RPT / 4; ++c4) {
+            for (int s = 0; s < splits; ++s) {
+                const float4 v = *reinterpret_cast<const float4*>(Bparts + ((int64_t)s * ncol + col) * KP + lig * RPT + 4 * c4);
+                b[4 * c4 + 0] += v.x; b[4 * c4 + 1] += v.y; b[4 * c4 + 2] += v.z; b[4 * c4 + 3] += v.w;
+            }
+            const float4 v = *reinterpret_cast<const float4*>(X + col * KP + lig * RPT + 4 * c4);
+            x[4 * c4 + 0] = v.x; x[4 * c4 + 1] = v.y; x[4 * c4 + 2] = v.z; x[4 * c4 + 3] = v.w;
+        }
+    }
+    bool active = solve && owner_warp;
+    if (__any_sync(0xffffffffu, active)) {
+#pragma unroll
+        for (int c = 0; c < RPT; ++c) {
+            const float4* g4 = reinterpret_cast<const float4*>(gram_f + (lig * RPT + c) * KP);
+#pragma unroll
+            for (int i4 = 0; i4 < KP / 4; ++i4) {
+                const float4 v = g4[i4];
+                a[c][4 * i4 + 0] = v.x - a[c][4 * i4 + 0];
+                a[c][4 * i4 + 1] = v.y - a[c][4 * i4 + 1];
+                a[c][4 * i4 + 2] = v.z - a[c][4 * i4 + 2];
+                a[c][4 * i4 + 3] = v.w - a[c][4 * i4 + 3];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < KP; ++i)  // diagonal element of row i lives on lane i / RPT, slot i % RPT
+            if (i / RPT == lig) inv[i % RPT] = (i < k) ? 1.0f / a[i % RPT][i] : 0.f;  // padding coordinates are inert
+
+        // Coordinate loop: at step i every lane runs the branch-free scalar step on its slot i % RPT, the
+        // owner lane (i / RPT) of each group broadcasts its multiplier with one width-L shuffle, and every
+        // lane applies it to its RPT entries of b. A lane's coordinates are consecutive, so it keeps the
+        // reference's running tol (reset to 1 by a clamp event, src/singlet.cpp:240-246) locally and the
+        // group's value is rebuilt after the sweep: the lanes from the last one with an event onwards add up.
+        float tol_g = 1.f;
+        const float kf = (float)k;
+        for (int sweep = 0; sweep < NNLS_MAX_SWEEPS; ++sweep) {
+            active = active && (tol_g / kf > 1e-8f);
+            if (!__any_sync(0xffffffffu, active)) break;
+            // Critical path of a step: b -> diff -> m -> shuffle -> b, nothing else is computed inside the sweep:
+            // m = min(-diff, x) is `clamp ? x : -diff` and x_new = max(x + diff, 0) is `clamp ? 0 : x + diff` in one
+            // FMNMX each; c0 = L2 * x - L1 does not depend on b (exact no-ops when L1 / L2 are 0, App. A-5).
+            // The owner lane keeps diff and the old x of its coordinates; the tol bookkeeping is replayed from
+            // them after the sweep (each coordinate is visited exactly once per sweep).
+            float xo[RPT], dv[RPT];
+#pragma unroll
+            for (int c = 0; c < RPT; ++c) { xo[c] = x[c]; dv[c] = 0.f; }
+#pragma unroll
+            for (int o = 0; o < L; ++o) {
+                const bool mine = active && (lig == o);  // a finished column is frozen: x stays, its b is dead
+                if constexpr (L == 1) {
+#pragma unroll
+                    for (int c = 0; c < RPT; ++c) {
+                        if (c < k) {  // uniform
+                            const float xi = x[c];
+                            const float c0 = fmaf(L2, xi, -L1);
+                            const float diff = fmaf(b[c], inv[c], c0);
+                            const float mult = fminf(-diff, xi);
+                            const float xnew = fmaxf(xi + diff, 0.f);
+                            x[c] = mine ? xnew : xi;
+                            dv[c] = mine ? diff : dv[c];
+#pragma unroll
+                            for (int cc = 0; cc < RPT; ++cc) b[cc] = fmaf(a[cc][c], mult, b[cc]);
+                        }
+                    }
+                } else {
+                    // Phase A: lane o runs its RPT consecutive coordinates on a private copy of its b entries, applying
+                    // its own multipliers to the later entries directly, so no shuffle sits between two of its steps.
+                    // Phase B: the RPT multipliers are broadcast (the shuffles overlap) and every lane, lane o included,
+                    // applies them to b in coordinate order -- the values are bit-identical to the step-by-step order.
+                    // A padding coordinate (i >= k, only in the last block) is inert: its b, x, inv and Gram entries are
+                    // zero, so diff = -L1, m = 0 and nothing changes; only whole blocks are skipped, so that no branch
+                    // separates the shuffles from each other.
+                    if (o * RPT < k) {  // uniform
+                        float bl[RPT], mo[RPT];
+#pragma unroll
+                        for (int c = 0; c < RPT; ++c) bl[c] = b[c];
+#pragma unroll
+                        for (int c = 0; c < RPT; ++c) {
+                            const int i = o * RPT + c;
+                            const float xi = x[c];
+                            const float c0 = fmaf(L2, xi, -L1);
+                            const float diff = fmaf(bl[c], inv[c], c0);
+                            mo[c] = fminf(-diff, xi);
+                            const float xnew = fmaxf(xi + diff, 0.f);
+                            x[c] = mine ? xnew : xi;
+                            dv[c] = mine ? diff : dv[c];
+#pragma unroll
+                            for (int cc = c + 1; cc < RPT; ++cc) bl[cc] = fmaf(a[cc][i], mo[c], bl[cc]);
+                        }
+                        float mult[RPT];
+#pragma unroll
+                        for (int c = 0; c < RPT; ++c) mult[c] = __shfl_sync(0xffffffffu, mo[c], o, L);
+#pragma unroll
+                        for (int c = 0; c < RPT; ++c)
+#pragma unroll
+                            for (int cc = 0; cc < RPT; ++cc) b[cc] = fmaf(a[cc][o * RPT + c], mult[c], b[cc]);
+                    }
+                }
+            }
+            // replay of the reference's running tol over my (consecutive) coordinates: a clamp event that changes
+            // x resets it to 1, every other step adds |diff / (x_new + 1e-15)| (src/singlet.cpp:240-246)
+            float ltol = 0.f;
+            bool lev = false;
+#pragma unroll
+            for (int c = 0; c < RPT; ++c) {
+                const bool clamp = (-dv[c] > xo[c]);
+                const bool clamp_ev = clamp && (xo[c] != 0.f);
+                float r;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x[c] + 1e-15f));
+                const float term = clamp ? 0.f : fabsf(dv[c] * r);
+                lev = lev || clamp_ev;
+                ltol = clamp_ev ? 1.f : ltol + term;
+            }
+            float part = ltol;
+            if constexpr (L > 1) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, lev);
+                const uint32_t gm = (bal >> (gi * L)) & ((1u << L) - 1u);
+                const int hl = gm ? (31 - __clz(gm)) : 0;  // last lane of my group with an event
+                part = (lig >= hl) ? ltol : 0.f;
+#pragma unroll
+                for (int o = 1; o < L; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            }
+            if (active) tol_g = part;
+        }
+    }
+
+    // ---- write back, per-CTA row sums (the local part of scale's d) ----
+    if (solve && owner_warp) {
+#pragma unroll
+        for (int c4 = 0; c4 < RPT / 4; ++c4)
+            *reinterpret_cast<float4*>(X + col * KP + lig * RPT + 4 * c4) = make_float4(x[4 * c4], x[4 * c4 + 1], x[4 * c4 + 2], x[4 * c4 + 3]);
+    }
+#pragma unroll
+    for (int c = 0; c < RPT; ++c) {
+        double v = (in_range && owner_warp) ? (double)x[c] : 0.0;
+#pragma unroll
+        for (int o = L; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (gi == 0) sred[warp][lig * RPT + c] = v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < KP; t += WARPS * 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) s += sred[w][t];
+        rowsum_part[(int64_t)blockIdx.x * KP + t] = s;
+    }
+}
+
 // generic masked fallback for KP = 128: a_i, b, x in shared memory (one warp per CTA, padded rows)
 __global__ void __launch_bounds__(32)
 nnls_masked_big_kernel(const float* __restrict__ Bparts, int splits, float* __restrict__ X,

