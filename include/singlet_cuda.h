@@ -109,6 +109,26 @@ int sgl_ard_nmf(sgl_handle* h, const sgl_csc* A, int nA, const sgl_csc* At, int 
                 uint64_t inv_density, double overfit_threshold, uint16_t trace_test_mse, sgl_trace* trace,
                 const sgl_callbacks* cb);
 
+/* Rank-search batching: the fits of a cross-validation sweep -- the loop over
+ * (rank, replicate) of R/cross_validate_nmf.R:69-97 and R/ard_nmf.R:95-159, one c_ard_nmf call each -- are
+ * independent given A, so the library runs `concurrency` of them at a time on private streams (each of
+ * these small fits is latency-bound and leaves most of the chip idle). A and At are uploaded once and
+ * shared; every worker keeps its own mask and factor buffers. Results are bit-identical to n_jobs
+ * sequential sgl_ard_nmf calls. concurrency <= 0 lets the library choose (bounded by free device
+ * memory). cb->poll_interrupt is polled on the calling thread while the workers run; on_iter is not used. */
+typedef struct sgl_fit_job {
+    int32_t k;        /* rank of this fit */
+    int32_t status;   /* out: SGL_OK or this fit's error code */
+    uint64_t seed;    /* mask seed (rng state) of this fit */
+    double* w;        /* k x m in (w_init) / out */
+    double* d;        /* k out */
+    double* h;        /* k x n out */
+    sgl_trace* trace; /* out, capacity set by the caller */
+} sgl_fit_job;
+int sgl_ard_nmf_batch(sgl_handle* h, const sgl_csc* A, int nA, const sgl_csc* At, int nAt, double tol, uint16_t maxit,
+                      double L1, double L2, uint64_t inv_density, double overfit_threshold, uint16_t trace_test_mse,
+                      sgl_fit_job* jobs, int32_t n_jobs, int32_t concurrency, const sgl_callbacks* cb);
+
 /* Dense-input variants c_nmf_dense / c_ard_nmf_dense: src/singlet.cpp:1051-1054, 1357-1361 (RcppExports.cpp:241-260,
  * 329-350) with predict / predict_mask / mse_test on Eigen::MatrixXd (:370-381, 506-531, 610-634). A is m x n, At is
  * n x m, column-major doubles. Every entry (zeros included) takes part, no column is skipped -- like the reference. */

@@ -41,6 +41,12 @@ class Trace(C.Structure):
                 ("capacity", C.c_int32), ("length", C.c_int32)]
 
 
+class FitJob(C.Structure):
+    """``sgl_fit_job``: one fit of a batched rank search (sgl_ard_nmf_batch)."""
+    _fields_ = [("k", C.c_int32), ("status", C.c_int32), ("seed", C.c_uint64), ("w", C.c_void_p), ("d", C.c_void_p),
+                ("h", C.c_void_p), ("trace", C.c_void_p)]
+
+
 _lib = None
 
 # every symbol include/singlet_cuda.h declares: (name, restype, argtypes)
@@ -62,6 +68,7 @@ SYMBOLS = [
                               _vp, _vp]),
     ("sgl_ard_nmf", _i32, [_vp, _vp, _i32, _vp, _i32, _dbl, _u16, _dbl, _dbl, _i32, _vp, _vp, _vp, _u64, _u64, _dbl, _u16,
                            _vp, _vp]),
+    ("sgl_ard_nmf_batch", _i32, [_vp, _vp, _i32, _vp, _i32, _dbl, _u16, _dbl, _dbl, _u64, _dbl, _u16, _vp, _i32, _i32, _vp]),
     ("sgl_nmf_dense", _i32, [_vp, _vp, _vp, _i64, _i64, _dbl, _u16, _dbl, _dbl, _dbl, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("sgl_ard_nmf_dense", _i32, [_vp, _vp, _vp, _i64, _i64, _dbl, _u16, _dbl, _dbl, _i32, _vp, _vp, _vp, _u64, _u64, _dbl, _u16,
                                  _vp, _vp]),

@@ -280,6 +280,43 @@ def c_ard_nmf(A, At, tol, maxit, verbose, L1, L2, threads, w, seed, inv_density,
             "score_overfit": so[:q].copy()}
 
 
+def c_ard_nmf_batch(A, At, tol, maxit, L1, L2, threads, ws, seeds, inv_density, overfit_threshold, trace_test_mse,
+                    concurrency: int = 0, handle: Handle | None = None):
+    """Batched ``c_ard_nmf``: the independent fits of a rank search -- the (rank, replicate)
+    loop of reference R/cross_validate_nmf.R:69-97 -- run ``concurrency`` at a time inside the library
+    (``sgl_ard_nmf_batch``), sharing one uploaded A / At. ``ws`` is a list of k_j x m initial factors and ``seeds``
+    the mask seed of each fit; returns one ``c_ard_nmf`` result dict per fit, bit-identical to sequential calls."""
+    h = handle or default_handle()
+    A, At = _as_csc(A), _as_csc(At)
+    a, na, k1 = _lib.chunks_to_c(A)
+    at, nat, k2 = _lib.chunks_to_c(At)
+    m, n = _nrows(A), _ncols(A)
+    cap = (int(maxit) & 0xFFFF) + 2
+    jobs = (_lib.FitJob * len(ws))()
+    outs, keep = [], []
+    for j, (w, seed) in enumerate(zip(ws, seeds)):
+        wk = np.array(w, dtype=np.float64, order="F")
+        k = wk.shape[0]
+        if wk.shape[1] != m:
+            raise ValueError("w must have nrow(A) columns")
+        d, hh = np.zeros(k), np.zeros((k, n), order="F")
+        mse, ft, so, it = np.zeros(cap), np.zeros(cap), np.zeros(cap), np.zeros(cap, np.int32)
+        tr = _lib.Trace(mse.ctypes.data, it.ctypes.data, ft.ctypes.data, so.ctypes.data, cap, 0)
+        keep.append(tr)
+        jobs[j] = _lib.FitJob(k, 0, int(seed) & 0xFFFFFFFFFFFFFFFF, wk.ctypes.data, d.ctypes.data, hh.ctypes.data, C.addressof(tr))
+        outs.append((wk, d, hh, mse, it, ft, so, tr))
+    cb, keep_cb = _callbacks(False, True)
+    _lib.check(h.lib.sgl_ard_nmf_batch(h.ptr, a, na, at, nat, float(tol), int(maxit) & 0xFFFF, float(L1), float(L2),
+                                       int(inv_density), float(overfit_threshold), int(trace_test_mse) & 0xFFFF, jobs, len(ws),
+                                       int(concurrency), C.addressof(cb) if cb is not None else None))
+    res = []
+    for wk, d, hh, mse, it, ft, so, tr in outs:
+        q = tr.length
+        res.append({"w": wk, "d": d, "h": hh, "test_mse": mse[:q].copy(), "iter": it[:q].copy(), "tol": ft[:q].copy(),
+                    "score_overfit": so[:q].copy()})
+    return res
+
+
 def c_ard_nmf_sparse_list(A_, At_, tol, maxit, verbose, L1, L2, threads, w, rng_seed, inv_density, overfit_threshold,
                           trace_test_mse, handle: Handle | None = None):
     """``c_ard_nmf_sparse_list`` (reference src/singlet.cpp:1162-1234)."""
@@ -381,9 +418,14 @@ def project_model(A, w, L1=0.01, L2=0, threads=0, handle: Handle | None = None):
 
 
 def cross_validate_nmf(A, ranks, n_replicates=3, tol=1e-4, maxit=100, verbose=1, L1=0.01, L2=0, threads=0,
-                       test_density=0.05, tol_overfit=1e-4, trace_test_mse=5, rng=None, handle: Handle | None = None):
+                       test_density=0.05, tol_overfit=1e-4, trace_test_mse=5, rng=None, handle: Handle | None = None,
+                       batch: bool = True, concurrency: int = 0):
     """``cross_validate_nmf`` (reference R/cross_validate_nmf.R:18-105). Returns a pandas DataFrame with
-    columns ``k, rep, test_error, iter, tol`` (one row per traced iteration of every fit)."""
+    columns ``k, rep, test_error, iter, tol`` (one row per traced iteration of every fit).
+
+    ``batch`` (default) hands the whole (rank, replicate) grid to ``sgl_ard_nmf_batch``, which runs several of the
+    independent fits at a time on the device; the rows are identical to the fit-by-fit loop (``batch=False``, also
+    used when ``verbose > 1`` so that every fit can print its trace like the reference)."""
     if L1 >= 1:
         raise ValueError("L1 penalty must be strictly in the range (0, 1]")
     r = _rng(rng)
@@ -400,6 +442,17 @@ def cross_validate_nmf(A, ranks, n_replicates=3, tol=1e-4, maxit=100, verbose=1,
         m = A.shape[0]
     w_init = [r.matrix_runif(max(ranks), m) for _ in range(n_replicates)]
     rows = []
+    inv_density = int(round(1 / test_density))
+    if batch and verbose <= 1:
+        grid = [(k, rep) for rep in range(1, n_replicates + 1) for k in ranks]
+        seeds = [abs(r.dot_random_seed(3 + rep)) for _, rep in grid]
+        models = c_ard_nmf_batch(A, At, tol, maxit, L1, L2, threads, [w_init[rep - 1][:k, :] for k, rep in grid], seeds,
+                                 inv_density, tol_overfit, trace_test_mse, concurrency, handle)
+        for (k, rep), model in zip(grid, models):
+            for q in range(len(model["test_mse"])):
+                rows.append({"k": k, "rep": rep, "test_error": model["test_mse"][q], "iter": int(model["iter"][q]),
+                             "tol": model["tol"][q]})
+        return pd.DataFrame(rows, columns=["k", "rep", "test_error", "iter", "tol"])
     # expand.grid(k = ranks, rep = 1:n_replicates): k varies fastest
     for rep in range(1, n_replicates + 1):
         for k in ranks:

@@ -9,7 +9,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -72,7 +76,8 @@ struct sgl_matrix {
     int64_t nrow = 0, ncol = 0, nnz = 0;
     int64_t* colptr = nullptr;  // ncol + 1
     uint2* rec = nullptr;       // nnz records {row, value bits}
-    std::map<int, TileIndex> tiles;  // per padded rank
+    std::map<int, TileIndex> tiles;  // per padded rank (built lazily under tiles_mu: batch workers share the matrix)
+    std::mutex tiles_mu;
     uint64_t fingerprint = 0;        // host-buffer identity for the upload cache
 };
 
@@ -122,6 +127,8 @@ struct sgl_handle {
     sgl_matrix* cAt = nullptr;
     sgl_mask* cmA = nullptr;
     sgl_mask* cmAt = nullptr;
+    // workers of sgl_ard_nmf_batch: child handles (own stream, scratch, masks) that share cA / cAt
+    std::vector<sgl_handle*> children;
 };
 
 namespace sgl {
@@ -415,6 +422,7 @@ static int matrix_from_dense(sgl_handle* h, const double* D, int64_t nrow, int64
 
 // tile index for padded rank KP (lazily built, cached on the matrix)
 static int get_tiles(sgl_handle* h, sgl_matrix* m, int kpv, const TileIndex** out) {
+    std::lock_guard<std::mutex> lock(m->tiles_mu);  // handles that share the matrix build an index once
     auto it = m->tiles.find(kpv);
     if (it != m->tiles.end()) {
         *out = &it->second;
@@ -458,6 +466,7 @@ static int get_tiles(sgl_handle* h, sgl_matrix* m, int kpv, const TileIndex** ou
     m->tiles[kpv] = ti;
     TileIndex& ref = m->tiles[kpv];
     SGL_TRY(build_stream(h, m, ref, m->rec, &ref.stream));
+    SGL_CUDA(cudaStreamSynchronize(h->stream));  // complete before another handle's stream may read it
     *out = &ref;
     return SGL_OK;
 }
@@ -630,25 +639,32 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
             // one-group-per-warp grid would leave most SMs without work
             int G = 1;
             DISPATCH_KP(KPV, G = (KP <= 32) ? MaskedSubCfg<(KP <= 32 ? KP : 32)>::G : 1);
-            const int64_t ctas1 = (ncol + 4 * G - 1) / (4 * G);
-            const bool share = ctas1 < 2 * (int64_t)h->sm_count;
-            n_parts = share ? (ncol + G - 1) / G : ctas1;
+            // one column group per warp (4 groups per CTA) when there are plenty of columns; otherwise the 4 or 2
+            // warps of a CTA share a group (split its held-out lists), picking the widest sharing whose grid --
+            // one CTA per group -- still fits on the chip in one wave (3 CTAs of 128 threads or 6 of 64 per SM).
+            const int64_t n_groups = (ncol + G - 1) / G;
+            int ws = 1;
+            if (n_groups <= 3 * (int64_t)h->sm_count) ws = 4;
+            else if (n_groups <= 6 * (int64_t)h->sm_count) ws = 2;
+            static const char* dbg_share = getenv("SGL_MASKED_SHARE");  // debug: force 1 / 2 / 4
+            if (dbg_share && (dbg_share[0] == '1' || dbg_share[0] == '2' || dbg_share[0] == '4')) ws = dbg_share[0] - '0';
+            n_parts = ws == 1 ? (n_groups + 3) / 4 : n_groups;
             SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
             switch (KPV) {
+#define MASKED_SUB_LAUNCH(KPC, WSC, THREADS)                                                                        \
+    nnls_masked_sub_kernel<KPC, WSC><<<(unsigned)n_parts, THREADS, 0, h->stream>>>(                                   \
+        Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, mask->mptr, mask->mrec, ncol, k, (float)L1, (float)L2, \
+        h->part.p)
 #define MASKED_SUB_CASE(KPC)                                                                                        \
     case KPC:                                                                                                       \
-        if (share)                                                                                                  \
-            nnls_masked_sub_kernel<KPC, 4><<<(unsigned)n_parts, 128, 0, h->stream>>>(                                \
-                Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, mask->mptr, mask->mrec, ncol, k, (float)L1, \
-                (float)L2, h->part.p);                                                                              \
-        else                                                                                                        \
-            nnls_masked_sub_kernel<KPC, 1><<<(unsigned)n_parts, 128, 0, h->stream>>>(                                \
-                Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, mask->mptr, mask->mrec, ncol, k, (float)L1, \
-                (float)L2, h->part.p);                                                                              \
+        if (ws == 4) MASKED_SUB_LAUNCH(KPC, 4, 128);                                                                \
+        else if (ws == 2) MASKED_SUB_LAUNCH(KPC, 2, 64);                                                            \
+        else MASKED_SUB_LAUNCH(KPC, 1, 128);                                                                        \
         break;
                 MASKED_SUB_CASE(4) MASKED_SUB_CASE(8) MASKED_SUB_CASE(16) MASKED_SUB_CASE(32)
                 default: break;
 #undef MASKED_SUB_CASE
+#undef MASKED_SUB_LAUNCH
             }
         } else if (KPV <= 64) {
             const int warps = 4;
@@ -800,6 +816,7 @@ static int mask_build(sgl_handle* h, const sgl_matrix* X, uint64_t seed, uint64_
         unsigned long long held = 0;
         cudaMemcpyAsync(&held, h->held.p, sizeof(held), cudaMemcpyDeviceToHost, h->stream);
         // the training streams already laid out for some padded ranks are refilled from the new training copy
+        std::lock_guard<std::mutex> lock(const_cast<sgl_matrix*>(X)->tiles_mu);
         for (auto& kv : m->stream_train) {
             auto it = X->tiles.find(kv.first);
             if (it == X->tiles.end() || !kv.second) { rc = fail(SGL_EINVAL, "mask build: stale training stream"); break; }
@@ -871,6 +888,21 @@ static int factor_download(sgl_handle* h, const float* dev, int k, int64_t cols,
 // ---------------------------------------------------------------------------------------------
 // host-facing drivers
 // ---------------------------------------------------------------------------------------------
+// the masks (the handle's and its batch workers') that refer to the cached matrix about to be replaced
+static void drop_masks(sgl_handle* h, sgl_mask** mask_slot) {
+    const bool is_a = (mask_slot == &h->cmA);
+    if (*mask_slot) {
+        mask_release(*mask_slot);
+        *mask_slot = nullptr;
+    }
+    for (sgl_handle* c : h->children) {
+        sgl_mask** cs = is_a ? &c->cmA : &c->cmAt;
+        if (*cs) {
+            mask_release(*cs);
+            *cs = nullptr;
+        }
+    }
+}
 static int cached_upload(sgl_handle* h, const sgl_csc* chunks, int n, sgl_matrix** slot, sgl_mask** mask_slot,
                          sgl_matrix** out) {
     const uint64_t fp = fingerprint_chunks(chunks, n);
@@ -878,10 +910,7 @@ static int cached_upload(sgl_handle* h, const sgl_csc* chunks, int n, sgl_matrix
         *out = *slot;
         return SGL_OK;
     }
-    if (*mask_slot) {
-        mask_release(*mask_slot);
-        *mask_slot = nullptr;
-    }
+    drop_masks(h, mask_slot);
     if (*slot) {
         matrix_release(*slot);
         *slot = nullptr;
@@ -1032,6 +1061,8 @@ int sgl_destroy(sgl_handle* h) {
     if (!h) return SGL_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    for (sgl_handle* c : h->children) sgl_destroy(c);  // batch workers: own stream, scratch and masks, no matrices
+    h->children.clear();
     mask_release(h->cmA);
     mask_release(h->cmAt);
     matrix_release(h->cA);
@@ -1126,10 +1157,7 @@ static int cached_dense(sgl_handle* h, const double* D, int64_t nrow, int64_t nc
         *out = *slot;
         return SGL_OK;
     }
-    if (*mask_slot) {
-        mask_release(*mask_slot);
-        *mask_slot = nullptr;
-    }
+    drop_masks(h, mask_slot);
     if (*slot) {
         matrix_release(*slot);
         *slot = nullptr;
@@ -1303,6 +1331,112 @@ static int ard_on_device(sgl_handle* h, sgl_matrix* A, sgl_matrix* At, double to
         push(mse, iter_, tol_);
     }
     return fit_outputs(h, fb, k, A->nrow, A->ncol, w, d, h_out);
+}
+
+// ---- rank-search batching -------------------------------------------------
+int sgl_ard_nmf_batch(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, int nAt, double tol, uint16_t maxit, double L1,
+                      double L2, uint64_t inv_density, double overfit_threshold, uint16_t trace_test_mse, sgl_fit_job* jobs,
+                      int32_t n_jobs, int32_t concurrency, const sgl_callbacks* cb) {
+    if (!h || (n_jobs > 0 && !jobs) || n_jobs < 0) return fail(SGL_EINVAL, "sgl_ard_nmf_batch: bad argument");
+    if (trace_test_mse == 0) return fail(SGL_EINVAL, "trace_test_mse must be >= 1 (the reference divides by it)");
+    if (inv_density == 0) return fail(SGL_EINVAL, "inv_density must be >= 1");
+    for (int j = 0; j < n_jobs; ++j) {
+        jobs[j].status = SGL_OK;
+        if (!jobs[j].w || !jobs[j].d || !jobs[j].h || !jobs[j].trace) return fail(SGL_EINVAL, "sgl_ard_nmf_batch: NULL pointer in job %d", j);
+        SGL_TRY(check_k(jobs[j].k));
+    }
+    if (n_jobs == 0) return SGL_OK;
+    SGL_TRY(set_device(h));
+    sgl_matrix *A = nullptr, *At = nullptr;
+    SGL_TRY(cached_upload(h, A_, nA, &h->cA, &h->cmA, &A));
+    SGL_TRY(cached_upload(h, At_, nAt, &h->cAt, &h->cmAt, &At));
+    SGL_TRY(check_shapes(A, At));
+    // tile indices of every padded rank in the batch, built once up front
+    int n_kp = 0;
+    for (int kp = 4; kp <= SGL_MAX_RANK; kp *= 2) {
+        bool used = false;
+        for (int j = 0; j < n_jobs && !used; ++j) used = kp_of(jobs[j].k) == kp;
+        if (!used) continue;
+        ++n_kp;
+        const TileIndex* ti = nullptr;
+        SGL_TRY(get_tiles(h, A, kp, &ti));
+        SGL_TRY(get_tiles(h, At, kp, &ti));
+    }
+    // workers: bounded by the jobs, by 8, and by what the masks + training streams of a worker may take of the free memory
+    int conc = concurrency > 0 ? concurrency : 4;
+    {
+        size_t free_b = 0, total_b = 0;
+        SGL_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const double per_worker = 16.0 * (double)A->nnz * (1.0 + n_kp) + 16.0 * (double)A->nrow * (double)A->ncol / (double)inv_density +
+                                  64.0 * (double)(A->nrow + A->ncol) * SGL_MAX_RANK;
+        const int fit = (int)(0.5 * (double)free_b / (per_worker > 1.0 ? per_worker : 1.0));
+        if (conc > fit) conc = fit;
+    }
+    if (conc > 8) conc = 8;
+    if (conc > n_jobs) conc = n_jobs;
+    if (conc < 1) conc = 1;
+    while ((int)h->children.size() < conc) {
+        sgl_handle* c = nullptr;
+        SGL_TRY(sgl_create(h->device, nullptr, &c));
+        h->children.push_back(c);
+    }
+    // largest ranks first (they take longest), ties in caller order
+    std::vector<int> order((size_t)n_jobs);
+    for (int j = 0; j < n_jobs; ++j) order[(size_t)j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].k > jobs[b].k; });
+
+    std::atomic<int> next(0), stop(0), running(conc);
+    std::mutex err_mu;
+    std::string first_msg;
+    int first_rc = SGL_OK;
+    sgl_callbacks wcb;
+    wcb.user = &stop;
+    wcb.poll_interrupt = [](void* u) -> int { return static_cast<std::atomic<int>*>(u)->load(std::memory_order_relaxed); };
+    wcb.on_iter = nullptr;
+    auto worker = [&](sgl_handle* c) {
+        if (cudaSetDevice(c->device) == cudaSuccess) {
+            for (;;) {
+                const int q = next.fetch_add(1);
+                if (q >= n_jobs || stop.load()) break;
+                sgl_fit_job& job = jobs[order[(size_t)q]];
+                const int rc = ard_on_device(c, A, At, tol, maxit, L1, L2, job.k, job.w, job.d, job.h, job.seed, inv_density,
+                                             overfit_threshold, trace_test_mse, job.trace, &wcb);
+                job.status = rc;
+                if (rc != SGL_OK) {
+                    std::lock_guard<std::mutex> lock(err_mu);
+                    if (first_rc == SGL_OK) {
+                        first_rc = rc;
+                        first_msg = last_error();  // thread-local: hand it to the calling thread
+                    }
+                    stop.store(1);
+                    break;
+                }
+            }
+        } else {
+            std::lock_guard<std::mutex> lock(err_mu);
+            if (first_rc == SGL_OK) { first_rc = SGL_ECUDA; first_msg = "batch worker: cudaSetDevice failed"; }
+            stop.store(1);
+        }
+        running.fetch_sub(1);
+    };
+    std::vector<std::thread> pool;
+    for (int q = 0; q < conc; ++q) pool.emplace_back(worker, h->children[(size_t)q]);
+    bool interrupted = false;
+    while (running.load() > 0) {  // the callbacks belong to the calling thread
+        if (cb && cb->poll_interrupt && !interrupted && cb->poll_interrupt(cb->user)) {
+            interrupted = true;
+            stop.store(1);
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(2));
+    }
+    for (auto& th : pool) th.join();
+    for (int q = 0; q < conc; ++q) {
+        h->launches += h->children[(size_t)q]->launches;
+        h->children[(size_t)q]->launches = 0;
+    }
+    if (interrupted) return fail(SGL_EINTERRUPT, "interrupted");
+    if (first_rc != SGL_OK) return fail(first_rc, "%s", first_msg.c_str());
+    return SGL_OK;
 }
 
 // ---- c_project_model / Rcpp_predict ----------------------------------------------------------

@@ -16,6 +16,7 @@
 // as per-CTA double partials, reduced in a fixed order afterwards (deterministic).
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace sgl {
 
@@ -431,9 +432,10 @@ nnls_masked_kernel(const float* __restrict__ Bparts, int splits, float* __restri
 // column per thread). A coordinate step then costs the same ~20 instructions per WARP as in the
 // warp-per-column kernel above but advances G columns, and every lane does useful FMAs in the
 // Gram-correction phase. When there are too few columns to fill the chip (the H update of a small
-// matrix: few cells, long held-out lists) WS = 4 warps share one column group: each accumulates the
-// correction over a quarter of the held-out rows and warp 0 folds the partial sums through shared
-// memory before solving.
+// matrix: few cells, long held-out lists) the WS = 4 or 2 warps of a CTA share one column group: each
+// accumulates the correction over its share of the held-out rows and warp 0 folds the partial sums
+// through shared memory before solving. The host picks the largest WS whose grid is still resident
+// in one wave.
 #ifndef SGL_MASKED32_MINB
 #define SGL_MASKED32_MINB 3
 #endif
@@ -446,7 +448,7 @@ struct MaskedSubCfg {
 };
 
 template <int KP, int WS>
-__global__ void __launch_bounds__(MaskedSubCfg<KP>::WARPS * 32, SGL_MASKED32_MINB)
+__global__ void __launch_bounds__((WS == 2 ? 2 : MaskedSubCfg<KP>::WARPS) * 32, (WS == 2 ? 2 : 1) * SGL_MASKED32_MINB)
 nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __restrict__ X,
                        const float* __restrict__ gram_f,   // [KP][KP] jitter-free FP32 Gram
                        const float* __restrict__ F,        // gather factor [rows][KP]
@@ -454,8 +456,9 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
                        const uint2* __restrict__ mrec, int64_t ncol, int k, float L1, float L2,
                        double* __restrict__ rowsum_part) {
     using C = MaskedSubCfg<KP>;
-    constexpr int L = C::L, RPT = C::RPT, G = C::G, WARPS = C::WARPS;
-    constexpr int CG = WARPS / WS;  // column groups per CTA
+    constexpr int L = C::L, RPT = C::RPT, G = C::G;
+    constexpr int WARPS = (WS == 2) ? 2 : C::WARPS;  // WS = 1: four column groups per CTA; WS = 2 / 4: the CTA shares one
+    constexpr int CG = WARPS / WS;                   // column groups per CTA
     static_assert(WS == 1 || WS == WARPS, "a column group is owned by one warp or by the whole CTA");
     constexpr int D = (L == 1) ? 4 : 8;        // held-out rows in flight per column
     constexpr int CPL = (L > 1) ? 1 : KP / 4;  // 16-byte chunks of a factor row copied by one lane
@@ -608,14 +611,20 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
             }
         }
 #pragma unroll
-        for (int i = 0; i < KP; ++i)  // diagonal element of row i lives on lane i / RPT, slot i % RPT
-            if (i / RPT == lig) inv[i % RPT] = (i < k) ? 1.0f / a[i % RPT][i] : 0.f;  // padding coordinates are inert
+        for (int c = 0; c < RPT; ++c) {  // the diagonal element of my row lig*RPT + c is a[c][lig*RPT + c]: pick it with selects
+            float dia = 1.f;
+#pragma unroll
+            for (int o = 0; o < L; ++o) dia = (lig == o) ? a[c][o * RPT + c] : dia;
+            inv[c] = (lig * RPT + c < k) ? 1.0f / dia : 0.f;  // padding coordinates are inert
+        }
 
         // Coordinate loop: at step i every lane runs the branch-free scalar step on its slot i % RPT, the
         // owner lane (i / RPT) of each group broadcasts its multiplier with one width-L shuffle, and every
         // lane applies it to its RPT entries of b. A lane's coordinates are consecutive, so it keeps the
         // reference's running tol (reset to 1 by a clamp event, src/singlet.cpp:240-246) locally and the
         // group's value is rebuilt after the sweep: the lanes from the last one with an event onwards add up.
+        auto sweeps = [&](auto has_l2) {
+        constexpr bool HAS_L2 = decltype(has_l2)::value;  // L2 == 0 (the default): c0 is the constant -L1
         float tol_g = 1.f;
         const float kf = (float)k;
         for (int sweep = 0; sweep < NNLS_MAX_SWEEPS; ++sweep) {
@@ -637,7 +646,7 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
                     for (int c = 0; c < RPT; ++c) {
                         if (c < k) {  // uniform
                             const float xi = x[c];
-                            const float c0 = fmaf(L2, xi, -L1);
+                            const float c0 = HAS_L2 ? fmaf(L2, xi, -L1) : -L1;
                             const float diff = fmaf(b[c], inv[c], c0);
                             const float mult = fminf(-diff, xi);
                             const float xnew = fmaxf(xi + diff, 0.f);
@@ -663,7 +672,7 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
                         for (int c = 0; c < RPT; ++c) {
                             const int i = o * RPT + c;
                             const float xi = x[c];
-                            const float c0 = fmaf(L2, xi, -L1);
+                            const float c0 = HAS_L2 ? fmaf(L2, xi, -L1) : -L1;
                             const float diff = fmaf(bl[c], inv[c], c0);
                             mo[c] = fminf(-diff, xi);
                             const float xnew = fmaxf(xi + diff, 0.f);
@@ -707,6 +716,8 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
             }
             if (active) tol_g = part;
         }
+        };
+        if (L2 == 0.f) sweeps(std::false_type{}); else sweeps(std::true_type{});
     }
 
     // ---- write back, per-CTA row sums (the local part of scale's d) ----

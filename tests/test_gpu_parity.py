@@ -468,3 +468,31 @@ def test_device_train_and_test_mse(oracle):
         assert abs(float(out[0]) / n - ref) <= 1e-5 * ref
     finally:
         be.close()
+
+
+def test_batched_rank_search_is_bit_identical_to_sequential_fits(handle):
+    """sgl_ard_nmf_batch (the (rank, replicate) loop of R/cross_validate_nmf.R:69-97 run several
+    fits at a time on private streams) returns exactly what one c_ard_nmf call per fit returns, in the caller's order,
+    and cross_validate_nmf(batch=True) builds the same data frame as the fit-by-fit loop."""
+    from singlet_b200 import api
+
+    A, At = _mk(300, 420, 0.1, 31)
+    rs = np.random.RandomState(5)
+    ranks = [2, 5, 9, 12, 17, 24, 3, 8]                     # every padded rank up to 32, not sorted
+    seeds = [11, 11, 11, 29, 29, 29, 2**40 + 7, 11]          # masks are re-seeded inside the workers
+    ws = [rs.uniform(size=(k, A.shape[0])) for k in ranks]
+    seq = [api.c_ard_nmf(A, At, 1e-5, 12, False, 0.01, 0.0, 0, w, s, 20, 1e-3, 3, handle) for w, s in zip(ws, seeds)]
+    for conc in (1, 3, 0):
+        bat = api.c_ard_nmf_batch(A, At, 1e-5, 12, 0.01, 0.0, 0, ws, seeds, 20, 1e-3, 3, conc, handle)
+        assert len(bat) == len(seq)
+        for b, s in zip(bat, seq):
+            for key in ("w", "d", "h", "test_mse", "iter", "tol", "score_overfit"):
+                assert np.array_equal(b[key], s[key]), key
+    api.set_seed(7)
+    df_b = api.cross_validate_nmf(A, [2, 6, 11], n_replicates=2, maxit=10, verbose=0, handle=handle, batch=True)
+    api.set_seed(7)
+    df_s = api.cross_validate_nmf(A, [2, 6, 11], n_replicates=2, maxit=10, verbose=0, handle=handle, batch=False)
+    assert df_b.equals(df_s)
+    # a bad job fails the call with that job's error, and an interrupt request stops the workers
+    with pytest.raises(Exception):
+        api.c_ard_nmf_batch(A, At, 1e-5, 12, 0.01, 0.0, 0, [np.ones((200, A.shape[0]))], [1], 20, 1e-3, 3, 2, handle)
