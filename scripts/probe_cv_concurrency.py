@@ -1,3 +1,4 @@
+"""Developer probe: cross_validate_nmf wall time on pbmc3k for a list of batch concurrencies (0 = fit by fit)."""
 import os, sys, time, json
 import numpy as np
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")

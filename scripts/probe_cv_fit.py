@@ -1,3 +1,4 @@
+"""Developer probe: wall time, iterations and per-kind GPU spans of single masked fits on pbmc3k (python scripts/probe_cv_fit.py 8,16,30 p)."""
 import os, sys, time, json
 import numpy as np
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
