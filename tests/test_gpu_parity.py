@@ -496,3 +496,4 @@ def test_batched_rank_search_is_bit_identical_to_sequential_fits(handle):
     # a bad job fails the call with that job's error, and an interrupt request stops the workers
     with pytest.raises(Exception):
         api.c_ard_nmf_batch(A, At, 1e-5, 12, 0.01, 0.0, 0, [np.ones((200, A.shape[0]))], [1], 20, 1e-3, 3, 2, handle)
+
