@@ -414,9 +414,16 @@ def e2e_leg(be, cfg, steps, A_dev, At_dev):
     h2d = (A.data.nbytes + A.indices.nbytes + A.indptr.nbytes + At.data.nbytes + At.indices.nbytes + At.indptr.nbytes
            + w0.nbytes)
     d2h = res["w"].nbytes + res["h"].nbytes + res["d"].nbytes + steps * 40
+    # informational: the same call with At = NULL (row f1: the library transposes A on the device, so only A crosses PCIe)
+    t0 = time.perf_counter()
+    res2 = api.c_nmf(A, None, 0.0, steps, False, L1, L1, L2, L2, 0, w0, h)
+    dt2 = time.perf_counter() - t0
+    same = bool(np.array_equal(res["w"], res2["w"]) and np.array_equal(res["h"], res2["h"]))
     h.close()
     return {"value": steps / dt, "unit": "iterations/s", "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
             "seconds_total": dt, "iterations": steps,
+            "device_transpose": {"value": steps / dt2, "seconds_total": dt2, "identical_model": same,
+                                 "h2d_bytes_per_step": (A.data.nbytes + A.indices.nbytes + A.indptr.nbytes + w0.nbytes) / steps},
             "note": "one sgl_nmf call: FP64 dgCMatrix A and At (pageable host memory) packed to 8-byte records by host "
                     "threads and uploaded through a pinned ring, K iterations, w/d/h downloaded; h2d_bytes_per_step counts "
                     "the host buffers handed to the call (12 B per non-zero), divided by K"}

@@ -90,7 +90,8 @@ int sgl_profile_read(sgl_handle* h, double* ms4, int64_t* counts4, int64_t* byte
 /* ---- host-facing entry points (one per reference routine) -------------------------------- */
 
 /* c_nmf / c_nmf_sparse_list: src/singlet.cpp:638-672, 715-743 (RcppExports.cpp:97-116, 138-155).
- * w: k x m in (w_init) / out; d: k out; h: k x n out. iters_out / tol_out may be NULL. */
+ * w: k x m in (w_init) / out; d: k out; h: k x n out. iters_out / tol_out may be NULL.
+ * At may be NULL (nAt = 0): the transpose is then built on the device (sgl_matrix_transpose). */
 int sgl_nmf(sgl_handle* h, const sgl_csc* A, int nA, const sgl_csc* At, int nAt, double tol, uint16_t maxit,
             double L1_w, double L1_h, double L2_w, double L2_h, int k, double* w, double* d, double* h_out,
             int32_t* iters_out, double* tol_out, const sgl_callbacks* cb);
@@ -162,6 +163,11 @@ int sgl_padded_rank(int k);
 
 /* Upload a chunk list (concatenated by columns) and build the gather-tile index. */
 int sgl_matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl_matrix** out);
+/* Device-side transpose (replaces `Matrix::t(A)` of R/run_nmf.R:40, R/cross_validate_nmf.R:58,
+ * R/ard_nmf.R:81): a new device matrix holding m^T with sorted row indices, bit-identical to uploading the host
+ * transpose. m may have at most 57,000 rows (the gene dimension). The host-facing entry points (sgl_nmf, sgl_linked_nmf,
+ * sgl_ard_nmf, sgl_ard_nmf_batch) use it when At is NULL / nAt is 0. */
+int sgl_matrix_transpose(sgl_handle* h, const sgl_matrix* m, sgl_matrix** out);
 /* Deterministic synthetic sparse counts (exact rules in singlet_b200/synth.py),
  * generated on the device. Orientation 0: columns = cells [col0, col0+ncol) of the m x n matrix;
  * orientation 1: columns = genes [col0, col0+ncol) of its transpose. values_table: 8 floats. */

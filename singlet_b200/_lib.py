@@ -78,6 +78,7 @@ SYMBOLS = [
     ("sgl_mask_draw", _i32, [_vp, _u64, _u64, _vp, _vp, _i64, _vp]),
     ("sgl_padded_rank", _i32, [_i32]),
     ("sgl_matrix_upload", _i32, [_vp, _vp, _i32, C.POINTER(_vp)]),
+    ("sgl_matrix_transpose", _i32, [_vp, _vp, C.POINTER(_vp)]),
     ("sgl_matrix_synth", _i32, [_vp, _i64, _i64, _dbl, _u64, _i32, _i64, _i64, _vp, C.POINTER(_vp)]),
     ("sgl_matrix_synth_block", _i32, [_vp, _i64, _i64, _dbl, _u64, _i32, _i64, _i64, _i64, _i64, _vp, C.POINTER(_vp)]),
     ("sgl_matrix_colptr", _i32, [_vp, _vp, _vp]),

@@ -106,6 +106,26 @@ def _as_csc(A):
     raise TypeError("expected a scipy sparse matrix (dgCMatrix analogue) or a list of them")
 
 
+MAX_DEVICE_TRANSPOSE_ROWS = 57000  # sgl_matrix_transpose keeps one counter per row of A in shared memory
+
+
+def _at_chunks(At):
+    """``At`` for the C ABI: the caller's transpose, or (NULL, 0) to have it built on the device (row f1)."""
+    if At is None:
+        return None, 0, None
+    return _lib.chunks_to_c(_as_csc(At))
+
+
+def _host_t(A):
+    At = A.T.tocsc()
+    At.sort_indices()
+    return At
+
+
+def _host_transpose_needed(A, device_transpose):
+    return not device_transpose or _nrows(A) > MAX_DEVICE_TRANSPOSE_ROWS
+
+
 def _ncols(A):
     if isinstance(A, list):
         return sum(_ncols(a) for a in A)
@@ -148,9 +168,9 @@ def c_nmf(A, At, tol, maxit, verbose, L1_w, L1_h, L2_w, L2_h, threads, w, handle
     ignored (the GPU replaces the OpenMP team). Returns ``{"w": k x m, "d": k, "h": k x n}`` plus the
     extra keys ``iter`` and ``tol`` (final values; the reference only prints them)."""
     h = handle or default_handle()
-    A, At = _as_csc(A), _as_csc(At)
+    A = _as_csc(A)
     a, na, k1 = _lib.chunks_to_c(A)
-    at, nat, k2 = _lib.chunks_to_c(At)
+    at, nat, k2 = _at_chunks(At)
     wk = np.array(w, dtype=np.float64, order="F")
     if wk.ndim != 2:
         raise ValueError("w must be a k x m matrix")
@@ -221,9 +241,9 @@ def c_linked_nmf(A, At, tol, maxit, verbose, L1, L2, threads, w, link_h, link_w,
     multiplied by a column of ``link_h`` / ``link_w`` before every solve (``predict_link`` :416-433). A side is
     linked only when its matrix has one column per cell / per gene, like the reference."""
     h = handle or default_handle()
-    A, At = _as_csc(A), _as_csc(At)
+    A = _as_csc(A)
     a, na, k1 = _lib.chunks_to_c(A)
-    at, nat, k2 = _lib.chunks_to_c(At)
+    at, nat, k2 = _at_chunks(At)
     wk = np.array(w, dtype=np.float64, order="F")
     k, m = wk.shape
     n = _ncols(A)
@@ -258,9 +278,9 @@ def c_ard_nmf(A, At, tol, maxit, verbose, L1, L2, threads, w, seed, inv_density,
     """``c_ard_nmf`` (reference src/singlet.cpp:1155-1159; R/RcppExports.R:70-72). Returns
     ``w, d, h, test_mse, iter, tol, score_overfit`` like src/singlet.cpp:1144-1151."""
     h = handle or default_handle()
-    A, At = _as_csc(A), _as_csc(At)
+    A = _as_csc(A)
     a, na, k1 = _lib.chunks_to_c(A)
-    at, nat, k2 = _lib.chunks_to_c(At)
+    at, nat, k2 = _at_chunks(At)
     wk = np.array(w, dtype=np.float64, order="F")
     k, m = wk.shape
     if m != _nrows(A):
@@ -287,9 +307,9 @@ def c_ard_nmf_batch(A, At, tol, maxit, L1, L2, threads, ws, seeds, inv_density, 
     (``sgl_ard_nmf_batch``), sharing one uploaded A / At. ``ws`` is a list of k_j x m initial factors and ``seeds``
     the mask seed of each fit; returns one ``c_ard_nmf`` result dict per fit, bit-identical to sequential calls."""
     h = handle or default_handle()
-    A, At = _as_csc(A), _as_csc(At)
+    A = _as_csc(A)
     a, na, k1 = _lib.chunks_to_c(A)
-    at, nat, k2 = _lib.chunks_to_c(At)
+    at, nat, k2 = _at_chunks(At)
     m, n = _nrows(A), _ncols(A)
     cap = (int(maxit) & 0xFFFF) + 2
     jobs = (_lib.FitJob * len(ws))()
@@ -383,11 +403,12 @@ def _sort_model(model, rank):
 
 
 def run_nmf(A, rank, tol=1e-4, maxit=100, verbose=True, L1=0.01, L2=0, threads=0, compression_level=3, rng=None,
-            handle: Handle | None = None):
+            handle: Handle | None = None, device_transpose: bool = True):
     """``run_nmf`` (reference R/run_nmf.R:18-77). Returns ``{"w": m x k, "d": k, "h": k x n}`` sorted by
     ``d``. A list input is treated as column chunks and routed to ``c_nmf_sparse_list`` with a
     distributed transpose (the reference sends lists to its IVSparse development path, which is out
-    of scope: SURVEY.md 2.1)."""
+    of scope: SURVEY.md 2.1). ``device_transpose`` (default): ``t(A)`` of R/run_nmf.R:40 is built on the device
+    (``sgl_matrix_transpose``, bit-identical records) instead of on the host."""
     r = _rng(rng)
     L1 = (L1, L1) if np.isscalar(L1) else (L1[0], L1[1] if len(L1) == 2 else L1[0])
     L2 = (L2, L2) if np.isscalar(L2) else (L2[0], L2[1] if len(L2) == 2 else L2[0])
@@ -395,15 +416,14 @@ def run_nmf(A, rank, tol=1e-4, maxit=100, verbose=True, L1=0.01, L2=0, threads=0
         A = _as_csc(list(A))
         if len({a.shape[0] for a in A}) != 1:
             raise ValueError("number of rows in all provided 'A' matrices are not identical")
-        At = _distributed_transpose(A)
+        At = _distributed_transpose(A) if _host_transpose_needed(A, device_transpose) else None
         w_init = r.matrix_runif(rank, A[0].shape[0])
         model = c_nmf_sparse_list(A, At, tol, maxit, verbose, L1[0], L2[0], threads, w_init, handle)
     else:
         if verbose:
             print("running with sparse optimization")
         A = _as_csc(A)
-        At = A.T.tocsc()
-        At.sort_indices()
+        At = _host_t(A) if _host_transpose_needed(A, device_transpose) else None
         w_init = r.matrix_runif(rank, A.shape[0])
         model = c_nmf(A, At, tol, maxit, verbose, L1[0], L1[1], L2[0], L2[1], threads, w_init, handle)
     return _sort_model(model, rank)
@@ -419,7 +439,7 @@ def project_model(A, w, L1=0.01, L2=0, threads=0, handle: Handle | None = None):
 
 def cross_validate_nmf(A, ranks, n_replicates=3, tol=1e-4, maxit=100, verbose=1, L1=0.01, L2=0, threads=0,
                        test_density=0.05, tol_overfit=1e-4, trace_test_mse=5, rng=None, handle: Handle | None = None,
-                       batch: bool = True, concurrency: int = 0):
+                       batch: bool = True, concurrency: int = 0, device_transpose: bool = True):
     """``cross_validate_nmf`` (reference R/cross_validate_nmf.R:18-105). Returns a pandas DataFrame with
     columns ``k, rep, test_error, iter, tol`` (one row per traced iteration of every fit).
 
@@ -433,12 +453,11 @@ def cross_validate_nmf(A, ranks, n_replicates=3, tol=1e-4, maxit=100, verbose=1,
     sparse_list = isinstance(A, (list, tuple))
     if sparse_list:
         A = _as_csc(list(A))
-        At = _distributed_transpose(A)
+        At = _distributed_transpose(A) if _host_transpose_needed(A, device_transpose) else None
         m = A[0].shape[0]
     else:
         A = _as_csc(A)
-        At = A.T.tocsc()
-        At.sort_indices()
+        At = _host_t(A) if _host_transpose_needed(A, device_transpose) else None
         m = A.shape[0]
     w_init = [r.matrix_runif(max(ranks), m) for _ in range(n_replicates)]
     rows = []
@@ -499,7 +518,7 @@ def GetBestRank(df, tol_overfit=1e-4):
 
 def ard_nmf(A, k_init=2, k_max=100, k_min=2, n_replicates=1, tol=1e-5, cv_tol=1e-4, maxit=100, verbose=1, L1=0.01, L2=0,
             threads=0, test_density=0.05, learning_rate=1, tol_overfit=1e-3, trace_test_mse=1, rng=None,
-            handle: Handle | None = None):
+            handle: Handle | None = None, device_transpose: bool = True):
     """``ard_nmf`` (reference R/ard_nmf.R:31-193): rank search by cross-validated fits, then a final
     unmasked fit at the best rank. Returns the sorted model plus ``cv_data`` (DataFrame)."""
     if not L1 < 1:
@@ -512,12 +531,11 @@ def ard_nmf(A, k_init=2, k_max=100, k_min=2, n_replicates=1, tol=1e-5, cv_tol=1e
     sparse_list = isinstance(A, (list, tuple))
     if sparse_list:
         A = _as_csc(list(A))
-        At = _distributed_transpose(A)
+        At = _distributed_transpose(A) if _host_transpose_needed(A, device_transpose) else None
         m = A[0].shape[0]
     else:
         A = _as_csc(A)
-        At = A.T.tocsc()
-        At.sort_indices()
+        At = _host_t(A) if _host_transpose_needed(A, device_transpose) else None
         m = A.shape[0]
     w_init = [r.matrix_runif(k_max, m) for _ in range(n_replicates)]
     test_seed = abs(r.dot_random_seed(3))

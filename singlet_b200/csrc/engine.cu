@@ -922,6 +922,82 @@ static int cached_upload(sgl_handle* h, const sgl_csc* chunks, int n, sgl_matrix
     *out = m;
     return SGL_OK;
 }
+// X^T on the device (kernels in misc.cuh). X's row count must fit the per-row counters of one CTA
+// in shared memory (nrow <= 57,000: the gene dimension of A).
+static int transpose_on_device(sgl_handle* h, const sgl_matrix* X, sgl_matrix** out) {
+    const int64_t max_rows = (227 * 1024 - 1024) / 4;
+    if (X->nrow > max_rows)
+        return fail(SGL_EINVAL, "device transpose supports up to %lld rows (got %lld): pass At explicitly", (long long)max_rows, (long long)X->nrow);
+    if (X->ncol > 0x7fffffffLL) return fail(SGL_EINVAL, "device transpose: too many columns for int32 row indices of the transpose");
+    SGL_TRY(set_device(h));
+    sgl_matrix* t = new sgl_matrix();
+    t->nrow = X->ncol;
+    t->ncol = X->nrow;
+    t->nnz = X->nnz;
+    int n_blocks = 2 * h->sm_count;
+    if ((int64_t)n_blocks > X->ncol) n_blocks = (int)(X->ncol > 0 ? X->ncol : 1);
+    const int64_t cpb = (X->ncol + n_blocks - 1) / n_blocks;
+    n_blocks = (int)((X->ncol + cpb - 1) / (cpb > 0 ? cpb : 1));
+    if (n_blocks < 1) n_blocks = 1;
+    int32_t* blockcnt = nullptr;
+    int rc = SGL_OK;
+    do {
+        if (cudaMalloc(&t->colptr, sizeof(int64_t) * (size_t)(t->ncol + 1)) != cudaSuccess ||
+            cudaMalloc(&t->rec, sizeof(uint2) * (size_t)(t->nnz > 0 ? t->nnz : 1)) != cudaSuccess ||
+            cudaMalloc(&blockcnt, sizeof(int32_t) * (size_t)n_blocks * (size_t)X->nrow) != cudaSuccess) {
+            rc = fail(SGL_ENOMEM, "device transpose: cudaMalloc failed (%lld non-zeros)", (long long)X->nnz);
+            break;
+        }
+        if ((rc = h->counts.ensure((size_t)X->nrow + 2)) != SGL_OK) break;
+        const size_t smem = sizeof(int32_t) * (size_t)X->nrow;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(transpose_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            cudaFuncSetAttribute(transpose_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            attr_done = true;
+        }
+        transpose_count_kernel<<<n_blocks, 1024, smem, h->stream>>>(X->rec, X->colptr, X->ncol, X->nrow, cpb, blockcnt);
+        ++h->launches;
+        transpose_offsets_kernel<<<blocks_for(X->nrow, 256), 256, 0, h->stream>>>(blockcnt, X->nrow, n_blocks, h->counts.p);
+        ++h->launches;
+        exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->counts.p, X->nrow, t->colptr);
+        ++h->launches;
+        transpose_scatter_kernel<<<n_blocks, 1024, smem, h->stream>>>(X->rec, X->colptr, X->ncol, X->nrow, cpb, blockcnt, t->colptr, t->rec);
+        ++h->launches;
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(SGL_ECUDA, "device transpose: %s", cudaGetErrorString(e));
+    } while (0);
+    if (blockcnt) cudaFree(blockcnt);
+    if (rc != SGL_OK) {
+        matrix_release(t);
+        return rc;
+    }
+    *out = t;
+    return SGL_OK;
+}
+// At of the host-facing entry points: the caller's (cached upload) or, when none is given, the device transpose of A
+// cached in the same slot under a fingerprint derived from A's
+static int cached_At(sgl_handle* h, const sgl_csc* At_, int nAt, sgl_matrix* A, sgl_matrix** out) {
+    if (At_ && nAt > 0) return cached_upload(h, At_, nAt, &h->cAt, &h->cmAt, out);
+    const uint64_t fp = splitmix64(A->fingerprint ^ 0x7472616e73706f73ull);
+    if (h->cache && h->cAt && h->cAt->fingerprint == fp) {
+        *out = h->cAt;
+        return SGL_OK;
+    }
+    drop_masks(h, &h->cmAt);
+    if (h->cAt) {
+        matrix_release(h->cAt);
+        h->cAt = nullptr;
+    }
+    sgl_matrix* t = nullptr;
+    SGL_TRY(transpose_on_device(h, A, &t));
+    t->fingerprint = fp;
+    h->cAt = t;
+    *out = t;
+    return SGL_OK;
+}
+
 static int cached_mask(sgl_handle* h, const sgl_matrix* X, uint64_t seed, uint64_t inv, int mask_t, sgl_mask** slot,
                        sgl_mask** out) {
     if (*slot && (*slot)->X == X && (*slot)->seed == seed && (*slot)->inv_density == inv && (*slot)->mask_t == mask_t) {
@@ -1136,7 +1212,7 @@ int sgl_nmf(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, int nA
     SGL_TRY(set_device(h));
     sgl_matrix *A = nullptr, *At = nullptr;
     SGL_TRY(cached_upload(h, A_, nA, &h->cA, &h->cmA, &A));
-    SGL_TRY(cached_upload(h, At_, nAt, &h->cAt, &h->cmAt, &At));
+    SGL_TRY(cached_At(h, At_, nAt, A, &At));
     return nmf_on_device(h, A, At, tol, maxit, L1_w, L1_h, L2_w, L2_h, k, w, d, h_out, iters_out, tol_out, cb);
 }
 
@@ -1238,7 +1314,7 @@ int sgl_linked_nmf(sgl_handle* h, const sgl_csc* A_, const sgl_csc* At_, double 
     SGL_TRY(set_device(h));
     sgl_matrix *A = nullptr, *At = nullptr;
     SGL_TRY(cached_upload(h, A_, 1, &h->cA, &h->cmA, &A));
-    SGL_TRY(cached_upload(h, At_, 1, &h->cAt, &h->cmAt, &At));
+    SGL_TRY(cached_At(h, At_, At_ ? 1 : 0, A, &At));
     SGL_TRY(check_shapes(A, At));
     // src/singlet.cpp:1066-1067: a side is linked only when its matrix has one column per cell / gene
     const bool linking_h = link_h && lh_cols == A->ncol, linking_w = link_w && lw_cols == A->nrow;
@@ -1276,7 +1352,7 @@ int sgl_ard_nmf(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, in
     SGL_TRY(set_device(h));
     sgl_matrix *A = nullptr, *At = nullptr;
     SGL_TRY(cached_upload(h, A_, nA, &h->cA, &h->cmA, &A));
-    SGL_TRY(cached_upload(h, At_, nAt, &h->cAt, &h->cmAt, &At));
+    SGL_TRY(cached_At(h, At_, nAt, A, &At));
     return ard_on_device(h, A, At, tol, maxit, L1, L2, k, w, d, h_out, seed, inv_density, overfit_threshold, trace_test_mse, tr, cb);
 }
 
@@ -1349,7 +1425,7 @@ int sgl_ard_nmf_batch(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* A
     SGL_TRY(set_device(h));
     sgl_matrix *A = nullptr, *At = nullptr;
     SGL_TRY(cached_upload(h, A_, nA, &h->cA, &h->cmA, &A));
-    SGL_TRY(cached_upload(h, At_, nAt, &h->cAt, &h->cmAt, &At));
+    SGL_TRY(cached_At(h, At_, nAt, A, &At));
     SGL_TRY(check_shapes(A, At));
     // tile indices of every padded rank in the batch, built once up front
     int n_kp = 0;
@@ -1621,6 +1697,10 @@ int sgl_matrix_synth_block(sgl_handle* h, int64_t m_genes, int64_t n_cells, doub
     return SGL_OK;
 }
 
+int sgl_matrix_transpose(sgl_handle* h, const sgl_matrix* m, sgl_matrix** out) {
+    if (!h || !m || !out) return fail(SGL_EINVAL, "sgl_matrix_transpose: NULL argument");
+    return transpose_on_device(h, m, out);
+}
 int sgl_matrix_free(sgl_handle* h, sgl_matrix* m) {
     if (h) cudaSetDevice(h->device);
     matrix_release(m);

@@ -86,6 +86,13 @@ class CudaBackend:
         self._mats.append(m)
         return m
 
+    def transpose(self, mat):
+        """Device-side transpose of a device matrix (``sgl_matrix_transpose``)."""
+        m = C.c_void_p()
+        _lib.check(self.lib.sgl_matrix_transpose(self._h, mat, C.byref(m)))
+        self._mats.append(m)
+        return m
+
     def synth(self, m_genes, n_cells, density, seed, orientation, col0, ncol, table):
         table = np.ascontiguousarray(table, dtype=np.float32)
         m = C.c_void_p()

@@ -497,3 +497,38 @@ def test_batched_rank_search_is_bit_identical_to_sequential_fits(handle):
     with pytest.raises(Exception):
         api.c_ard_nmf_batch(A, At, 1e-5, 12, 0.01, 0.0, 0, [np.ones((200, A.shape[0]))], [1], 20, 1e-3, 3, 2, handle)
 
+
+def test_device_transpose_is_the_host_transpose(handle, oracle):
+    """sgl_matrix_transpose (SURVEY.md 8 row f1, replaces Matrix::t(A) of R/run_nmf.R:40): same column pointers, row
+    indices (sorted) and values as uploading scipy's transpose; fits with At = NULL are bit-identical to fits with the
+    host transpose, for single matrices and chunk lists, plain and masked."""
+    from singlet_b200 import api
+    from singlet_b200.sharded import CudaBackend
+
+    be = CudaBackend(0)
+    try:
+        for (m, n, dens, seed, empty) in ((300, 5000, 0.05, 3, (0, 7, 4999)), (57, 40, 0.3, 4, ()), (1, 9, 1.0, 5, ()), (2000, 333, 0.01, 6, (5,))):
+            A, At = _mk(m, n, dens, seed, empty_cols=empty)
+            dA = be.upload(A)
+            p, i, x, nrow, ncol = be.matrix_to_host(be.transpose(dA))
+            assert (nrow, ncol) == At.shape
+            assert np.array_equal(p, At.indptr) and np.array_equal(i, At.indices)
+            assert np.array_equal(x.astype(np.float32), At.data.astype(np.float32))
+    finally:
+        be.close()
+    A, At = _mk(400, 900, 0.06, 9)
+    w = np.random.RandomState(2).uniform(size=(7, 400))
+    a = api.c_nmf(A, At, 1e-6, 6, False, 0.01, 0.02, 0.0, 0.0, 0, w, handle)
+    b = api.c_nmf(A, None, 1e-6, 6, False, 0.01, 0.02, 0.0, 0.0, 0, w, handle)
+    c = api.c_nmf([A[:, :300].tocsc(), A[:, 300:].tocsc()], None, 1e-6, 6, False, 0.01, 0.02, 0.0, 0.0, 0, w, handle)
+    for key in ("w", "d", "h"):
+        assert np.array_equal(a[key], b[key]) and np.array_equal(a[key], c[key]), key
+    a = api.c_ard_nmf(A, At, 1e-6, 6, False, 0.01, 0.0, 0, w, 42, 20, 1e-3, 2, handle)
+    b = api.c_ard_nmf(A, None, 1e-6, 6, False, 0.01, 0.0, 0, w, 42, 20, 1e-3, 2, handle)
+    for key in ("w", "d", "h", "test_mse"):
+        assert np.array_equal(a[key], b[key]), key
+    api.set_seed(3)
+    m1 = api.run_nmf(A, 5, maxit=5, verbose=False, handle=handle, device_transpose=True)
+    api.set_seed(3)
+    m2 = api.run_nmf(A, 5, maxit=5, verbose=False, handle=handle, device_transpose=False)
+    assert np.array_equal(m1["w"], m2["w"]) and np.array_equal(m1["h"], m2["h"])
