@@ -165,8 +165,8 @@ int sgl_padded_rank(int k);
 int sgl_matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl_matrix** out);
 /* Device-side transpose (replaces `Matrix::t(A)` of R/run_nmf.R:40, R/cross_validate_nmf.R:58,
  * R/ard_nmf.R:81): a new device matrix holding m^T with sorted row indices, bit-identical to uploading the host
- * transpose. m may have at most 57,000 rows (the gene dimension). The host-facing entry points (sgl_nmf, sgl_linked_nmf,
- * sgl_ard_nmf, sgl_ard_nmf_batch) use it when At is NULL / nAt is 0. */
+ * transpose. One pass over the records per 57,856 rows of m (a single pass for A, whose rows are genes). The host-facing
+ * entry points (sgl_nmf, sgl_linked_nmf, sgl_ard_nmf, sgl_ard_nmf_batch) use it when At is NULL / nAt is 0. */
 int sgl_matrix_transpose(sgl_handle* h, const sgl_matrix* m, sgl_matrix** out);
 /* Deterministic synthetic sparse counts (exact rules in singlet_b200/synth.py),
  * generated on the device. Orientation 0: columns = cells [col0, col0+ncol) of the m x n matrix;

@@ -106,9 +106,6 @@ def _as_csc(A):
     raise TypeError("expected a scipy sparse matrix (dgCMatrix analogue) or a list of them")
 
 
-MAX_DEVICE_TRANSPOSE_ROWS = 57000  # sgl_matrix_transpose keeps one counter per row of A in shared memory
-
-
 def _at_chunks(At):
     """``At`` for the C ABI: the caller's transpose, or (NULL, 0) to have it built on the device (row f1)."""
     if At is None:
@@ -123,7 +120,7 @@ def _host_t(A):
 
 
 def _host_transpose_needed(A, device_transpose):
-    return not device_transpose or _nrows(A) > MAX_DEVICE_TRANSPOSE_ROWS
+    return not device_transpose
 
 
 def _ncols(A):

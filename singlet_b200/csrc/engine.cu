@@ -922,12 +922,10 @@ static int cached_upload(sgl_handle* h, const sgl_csc* chunks, int n, sgl_matrix
     *out = m;
     return SGL_OK;
 }
-// X^T on the device (kernels in misc.cuh). X's row count must fit the per-row counters of one CTA
-// in shared memory (nrow <= 57,000: the gene dimension of A).
+// X^T on the device (kernels in misc.cuh). One pass over the records per 57,856 rows of X (the per-row
+// counters of a CTA live in shared memory): a single pass for A (rows = genes), several for matrices with more rows.
 static int transpose_on_device(sgl_handle* h, const sgl_matrix* X, sgl_matrix** out) {
     const int64_t max_rows = (227 * 1024 - 1024) / 4;
-    if (X->nrow > max_rows)
-        return fail(SGL_EINVAL, "device transpose supports up to %lld rows (got %lld): pass At explicitly", (long long)max_rows, (long long)X->nrow);
     if (X->ncol > 0x7fffffffLL) return fail(SGL_EINVAL, "device transpose: too many columns for int32 row indices of the transpose");
     SGL_TRY(set_device(h));
     sgl_matrix* t = new sgl_matrix();
@@ -939,31 +937,48 @@ static int transpose_on_device(sgl_handle* h, const sgl_matrix* X, sgl_matrix** 
     const int64_t cpb = (X->ncol + n_blocks - 1) / n_blocks;
     n_blocks = (int)((X->ncol + cpb - 1) / (cpb > 0 ? cpb : 1));
     if (n_blocks < 1) n_blocks = 1;
+    const int64_t n_pass = (X->nrow + max_rows - 1) / max_rows;
+    const int64_t pass_rows = (X->nrow + n_pass - 1) / (n_pass > 0 ? n_pass : 1);
     int32_t* blockcnt = nullptr;
     int rc = SGL_OK;
     do {
         if (cudaMalloc(&t->colptr, sizeof(int64_t) * (size_t)(t->ncol + 1)) != cudaSuccess ||
             cudaMalloc(&t->rec, sizeof(uint2) * (size_t)(t->nnz > 0 ? t->nnz : 1)) != cudaSuccess ||
-            cudaMalloc(&blockcnt, sizeof(int32_t) * (size_t)n_blocks * (size_t)X->nrow) != cudaSuccess) {
+            cudaMalloc(&blockcnt, sizeof(int32_t) * (size_t)n_blocks * (size_t)(pass_rows > 0 ? pass_rows : 1)) != cudaSuccess) {
             rc = fail(SGL_ENOMEM, "device transpose: cudaMalloc failed (%lld non-zeros)", (long long)X->nnz);
             break;
         }
         if ((rc = h->counts.ensure((size_t)X->nrow + 2)) != SGL_OK) break;
-        const size_t smem = sizeof(int32_t) * (size_t)X->nrow;
+        const size_t smem = sizeof(int32_t) * (size_t)(pass_rows > 0 ? pass_rows : 1);
         static bool attr_done = false;
         if (!attr_done) {
             cudaFuncSetAttribute(transpose_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             cudaFuncSetAttribute(transpose_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             attr_done = true;
         }
-        transpose_count_kernel<<<n_blocks, 1024, smem, h->stream>>>(X->rec, X->colptr, X->ncol, X->nrow, cpb, blockcnt);
-        ++h->launches;
-        transpose_offsets_kernel<<<blocks_for(X->nrow, 256), 256, 0, h->stream>>>(blockcnt, X->nrow, n_blocks, h->counts.p);
-        ++h->launches;
+        // phase 1: row totals -> column pointers of X^T (with one pass the block offsets are kept for phase 2)
+        for (int64_t ps = 0; ps < n_pass; ++ps) {
+            const int64_t row0 = ps * pass_rows, nr = (row0 + pass_rows < X->nrow ? pass_rows : X->nrow - row0);
+            transpose_count_kernel<<<n_blocks, 1024, smem, h->stream>>>(X->rec, X->colptr, X->ncol, row0, nr, cpb, blockcnt);
+            ++h->launches;
+            transpose_offsets_kernel<<<blocks_for(nr, 256), 256, 0, h->stream>>>(blockcnt, nr, n_blocks, h->counts.p + row0);
+            ++h->launches;
+        }
         exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->counts.p, X->nrow, t->colptr);
         ++h->launches;
-        transpose_scatter_kernel<<<n_blocks, 1024, smem, h->stream>>>(X->rec, X->colptr, X->ncol, X->nrow, cpb, blockcnt, t->colptr, t->rec);
-        ++h->launches;
+        // phase 2: scatter, one row range at a time
+        for (int64_t ps = 0; ps < n_pass; ++ps) {
+            const int64_t row0 = ps * pass_rows, nr = (row0 + pass_rows < X->nrow ? pass_rows : X->nrow - row0);
+            if (n_pass > 1) {  // the offsets of this range were overwritten by the later ranges: recompute them
+                transpose_count_kernel<<<n_blocks, 1024, smem, h->stream>>>(X->rec, X->colptr, X->ncol, row0, nr, cpb, blockcnt);
+                ++h->launches;
+                transpose_offsets_kernel<<<blocks_for(nr, 256), 256, 0, h->stream>>>(blockcnt, nr, n_blocks, nullptr);
+                ++h->launches;
+            }
+            transpose_scatter_kernel<<<n_blocks, 1024, smem, h->stream>>>(X->rec, X->colptr, X->ncol, row0, nr, cpb, blockcnt, t->colptr,
+                                                                         t->rec);
+            ++h->launches;
+        }
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(SGL_ECUDA, "device transpose: %s", cudaGetErrorString(e));

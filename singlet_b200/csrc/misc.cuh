@@ -232,45 +232,51 @@ __global__ void factor_to_host_kernel(const float* __restrict__ src, int k, int 
 // Device-side transpose (`Matrix::t(A)`, R/run_nmf.R:40): column-compressed records of X
 // (nrow x ncol) -> column-compressed records of X^T with the rows of every column in ascending order, deterministic,
 // no sort. The columns of X are cut into blocks; a CTA owns one block and keeps one 32-bit counter per ROW of X in
-// shared memory (nrow <= ~57k: the gene dimension).
+// shared memory (up to ~57k rows -- the gene dimension -- per pass).
 //   1. count:   blockcnt[b][r] = non-zeros of row r inside column block b (shared-memory histogram)
 //   2. offsets: per row an exclusive scan over the blocks (in place) + the row totals -> column pointers of X^T
 //   3. scatter: the CTA walks its columns IN ORDER; the non-zeros of one column hit distinct rows, so they are placed
 //               in parallel with plain read-modify-writes of the per-row cursors, and a barrier separates columns:
 //               entries of a row arrive in ascending column order.
 // ----------------------------------------------------------------------------------------------
+// All three kernels work on the row range [row0, row0 + nr) of X (nr counters fit in shared memory); matrices with more
+// rows are transposed in several passes over the records.
 __global__ void __launch_bounds__(1024)
-transpose_count_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ colptr, int64_t ncol, int64_t nrow,
+transpose_count_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ colptr, int64_t ncol, int64_t row0, int64_t nr,
                        int64_t cols_per_block, int32_t* __restrict__ blockcnt) {
     extern __shared__ int32_t s_cnt[];
-    for (int64_t r = threadIdx.x; r < nrow; r += blockDim.x) s_cnt[r] = 0;
+    for (int64_t r = threadIdx.x; r < nr; r += blockDim.x) s_cnt[r] = 0;
     __syncthreads();
     const int64_t c0 = (int64_t)blockIdx.x * cols_per_block;
     const int64_t c1 = c0 + cols_per_block < ncol ? c0 + cols_per_block : ncol;
     if (c0 < c1) {
         const int64_t b = colptr[c0], e = colptr[c1];
-        for (int64_t p = b + threadIdx.x; p < e; p += blockDim.x) atomicAdd(&s_cnt[rec[p].x], 1);
+        for (int64_t p = b + threadIdx.x; p < e; p += blockDim.x) {
+            const int64_t r = (int64_t)rec[p].x - row0;
+            if (r >= 0 && r < nr) atomicAdd(&s_cnt[r], 1);
+        }
     }
     __syncthreads();
-    for (int64_t r = threadIdx.x; r < nrow; r += blockDim.x) blockcnt[(int64_t)blockIdx.x * nrow + r] = s_cnt[r];
+    for (int64_t r = threadIdx.x; r < nr; r += blockDim.x) blockcnt[(int64_t)blockIdx.x * nr + r] = s_cnt[r];
 }
-__global__ void transpose_offsets_kernel(int32_t* __restrict__ blockcnt, int64_t nrow, int n_blocks, int64_t* __restrict__ rowtot) {
+// per row: exclusive scan over the blocks (in place) and the row total
+__global__ void transpose_offsets_kernel(int32_t* __restrict__ blockcnt, int64_t nr, int n_blocks, int64_t* __restrict__ rowtot) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nrow) return;
+    if (r >= nr) return;
     int64_t run = 0;
     for (int b = 0; b < n_blocks; ++b) {
-        const int32_t c = blockcnt[(int64_t)b * nrow + r];
-        blockcnt[(int64_t)b * nrow + r] = (int32_t)run;  // a row holds < 2^31 non-zeros (it has at most ncol <= 2^31 - 1 entries)
+        const int32_t c = blockcnt[(int64_t)b * nr + r];
+        blockcnt[(int64_t)b * nr + r] = (int32_t)run;  // a row holds < 2^31 non-zeros (it has at most ncol <= 2^31 - 1 entries)
         run += c;
     }
-    rowtot[r] = run;
+    if (rowtot) rowtot[r] = run;
 }
 __global__ void __launch_bounds__(1024)
-transpose_scatter_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ colptr, int64_t ncol, int64_t nrow,
+transpose_scatter_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ colptr, int64_t ncol, int64_t row0, int64_t nr,
                          int64_t cols_per_block, const int32_t* __restrict__ blockoff, const int64_t* __restrict__ tptr,
                          uint2* __restrict__ trec) {
     extern __shared__ int32_t s_cur[];
-    for (int64_t r = threadIdx.x; r < nrow; r += blockDim.x) s_cur[r] = blockoff[(int64_t)blockIdx.x * nrow + r];
+    for (int64_t r = threadIdx.x; r < nr; r += blockDim.x) s_cur[r] = blockoff[(int64_t)blockIdx.x * nr + r];
     __syncthreads();
     const int64_t c0 = (int64_t)blockIdx.x * cols_per_block;
     const int64_t c1 = c0 + cols_per_block < ncol ? c0 + cols_per_block : ncol;
@@ -278,9 +284,12 @@ transpose_scatter_kernel(const uint2* __restrict__ rec, const int64_t* __restric
         const int64_t b = colptr[c], e = colptr[c + 1];
         for (int64_t p = b + threadIdx.x; p < e; p += blockDim.x) {
             const uint2 v = rec[p];
-            const int32_t slot = s_cur[v.x];  // rows of one column are distinct: no two threads touch the same cursor
-            s_cur[v.x] = slot + 1;
-            trec[tptr[v.x] + slot] = make_uint2((uint32_t)c, v.y);
+            const int64_t r = (int64_t)v.x - row0;
+            if (r >= 0 && r < nr) {
+                const int32_t slot = s_cur[r];  // rows of one column are distinct: no two threads touch the same cursor
+                s_cur[r] = slot + 1;
+                trec[tptr[v.x] + slot] = make_uint2((uint32_t)c, v.y);
+            }
         }
         __syncthreads();
     }

@@ -507,13 +507,16 @@ def test_device_transpose_is_the_host_transpose(handle, oracle):
 
     be = CudaBackend(0)
     try:
-        for (m, n, dens, seed, empty) in ((300, 5000, 0.05, 3, (0, 7, 4999)), (57, 40, 0.3, 4, ()), (1, 9, 1.0, 5, ()), (2000, 333, 0.01, 6, (5,))):
+        for (m, n, dens, seed, empty) in ((300, 5000, 0.05, 3, (0, 7, 4999)), (57, 40, 0.3, 4, ()), (1, 9, 1.0, 5, ()), (2000, 333, 0.01, 6, (5,)),
+                                          (130000, 260, 0.002, 7, (3,))):  # the last one needs three row-range passes
             A, At = _mk(m, n, dens, seed, empty_cols=empty)
             dA = be.upload(A)
             p, i, x, nrow, ncol = be.matrix_to_host(be.transpose(dA))
             assert (nrow, ncol) == At.shape
             assert np.array_equal(p, At.indptr) and np.array_equal(i, At.indices)
             assert np.array_equal(x.astype(np.float32), At.data.astype(np.float32))
+            p2, i2, x2, _, _ = be.matrix_to_host(be.transpose(be.transpose(dA)))  # and back again
+            assert np.array_equal(p2, A.indptr) and np.array_equal(i2, A.indices) and np.array_equal(x2.astype(np.float32), A.data.astype(np.float32))
     finally:
         be.close()
     A, At = _mk(400, 900, 0.06, 9)
