@@ -212,13 +212,18 @@ class ShardedNMF:
     def __init__(self, backend, m: int, n: int, k: int, A_shard, At_shard, rank: int = 0, world: int = 1, group=None,
                  mask_A=None, mask_At=None, layout: str = "A"):
         """layout "A": At_shard = this rank's genes over ALL cells. layout "B" (plain fits only): At_shard =
-        the transpose of this rank's own cell block (local cells x all genes)."""
+        the transpose of this rank's own cell block (local cells x all genes), or None to build it on the device."""
         self.be, self.m, self.n, self.k = backend, m, n, k
         self.rank, self.world, self.group = rank, world, group
-        self.A, self.At, self.mask_A, self.mask_At = A_shard, At_shard, mask_A, mask_At
         self.layout = layout
         if layout == "B" and (mask_A is not None or mask_At is not None):
             raise ValueError("layout B does not support the masked (CV) solve")
+        if At_shard is None:
+            # layout B: the transpose of the local cell block is built on the device (row f1), so a rank uploads only A
+            if layout != "B" and world > 1:
+                raise ValueError("layout A needs the gene block over all cells; only layout B can derive At_shard from A_shard")
+            At_shard = backend.transpose(A_shard)
+        self.A, self.At, self.mask_A, self.mask_At = A_shard, At_shard, mask_A, mask_At
         self.c0, self.c1, self.c_per = shard_bounds(n, world, rank)
         self.g0, self.g1, self.g_per = shard_bounds(m, world, rank)
         be = backend

@@ -25,6 +25,8 @@ def test_sharded_driver_world1_matches_c_driver(oracle):
         assert np.array_equal(s["w"], c["w"]) and np.array_equal(s["h"], c["h"]) and np.allclose(s["d"], c["d"], rtol=1e-12)
         sb = sharded_nmf(be, m, n, k, hA, hAt, w0, tol=0.0, maxit=6, L1=(0.01, 0.01), layout="B")  # world 1: At is the full transpose
         assert np.array_equal(sb["w"], c["w"]) and np.array_equal(sb["h"], c["h"])
+        sn = sharded_nmf(be, m, n, k, hA, None, w0, tol=0.0, maxit=6, L1=(0.01, 0.01), layout="B")  # transpose built on the device
+        assert np.array_equal(sn["w"], c["w"]) and np.array_equal(sn["h"], c["h"])
         sm = sharded_ard_nmf(be, m, n, k, hA, hAt, w0, 123, 20, tol=0.0, maxit=5, overfit_threshold=10.0, trace_test_mse=2)
         cm = api.c_ard_nmf(A, At, 0.0, 5, False, 0.01, 0, 0, w0, 123, 20, 10.0, 2)
         assert np.array_equal(sm["iter"], cm["iter"]) and np.allclose(sm["test_mse"], cm["test_mse"], rtol=1e-12)
