@@ -184,8 +184,27 @@ def cpu_reference_leg(cfg, steps, warmup, sample_cells, backend=None):
 
 
 # ------------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but C libraries print there too (NCCL prints "NCCL version ..." under
+    NCCL_DEBUG=VERSION): keep a private duplicate of the real stdout for the JSON line and point fd 1 at stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(obj) + "\n").encode())
+
+
 def main():
     args = parse()
+    _claim_stdout()
     cfg = CONFIGS[args.config]
     m, n, dens, k = cfg["m"], cfg["n"], cfg["density"], cfg["k"]
     rank = int(os.environ.get("RANK", "0"))
@@ -215,7 +234,7 @@ def main():
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": base_cfg, "cpu_baseline": cb,
                "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out))
+        _emit(out)
         return 0
 
     import torch
@@ -230,8 +249,6 @@ def main():
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's own log lines (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     be = CudaBackend(local_rank)
     table = synth.values_table(m, dens)
@@ -331,7 +348,7 @@ def main():
         if not args.no_cpu:
             be_cpu = be
             out["cpu_baseline"] = cpu_reference_leg(cfg, args.steps, args.warmup, args.cpu_sample_cells, be_cpu)
-        print(json.dumps(out))
+        _emit(out)
     be.close()
     if world > 1:
         dist.destroy_process_group()
