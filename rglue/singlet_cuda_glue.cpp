@@ -217,3 +217,46 @@ Eigen::MatrixXd Rcpp_predict(Rcpp::SparseMatrix A, Eigen::MatrixXd w, const doub
     check(sgl_predict(handle(), &a, 1, w.data(), w.rows(), w.cols(), L1, L2, h.data()));
     return h;
 }
+
+// Optional new export: the whole (rank, replicate) grid of R/cross_validate_nmf.R:69-97 in ONE call.
+// `w_inits` is a list of k_j x m matrices (the `w_init[[rep]][1:k, ]` slices the R loop passes one at a time), `seeds` the
+// matching `abs(.Random.seed[[3 + rep]])` values. Returns a list of the same model lists c_ard_nmf returns, in order.
+// The R loop body becomes:  models <- c_ard_nmf_batch(A, At, tol, maxit, L1, L2, threads, w_inits, seeds, inv_density, ...)
+//[[Rcpp::export]]
+Rcpp::List c_ard_nmf_batch(Rcpp::SparseMatrix& A, Rcpp::SparseMatrix& At, const double tol, const uint16_t maxit, const double L1,
+                           const double L2, const uint16_t threads, Rcpp::List w_inits, Rcpp::NumericVector seeds,
+                           const uint64_t inv_density, const double overfit_threshold, const uint16_t trace_test_mse) {
+    const int n_jobs = w_inits.size();
+    const int64_t n = A.cols();
+    const int cap = (int)maxit + 2;
+    std::vector<Eigen::MatrixXd> w(n_jobs), h(n_jobs);
+    std::vector<Eigen::VectorXd> d(n_jobs);
+    std::vector<std::vector<double>> mse(n_jobs), ft(n_jobs), so(n_jobs);
+    std::vector<std::vector<int32_t>> it(n_jobs);
+    std::vector<sgl_trace> tr(n_jobs);
+    std::vector<sgl_fit_job> jobs(n_jobs);
+    for (int j = 0; j < n_jobs; ++j) {
+        w[j] = Rcpp::as<Eigen::MatrixXd>(w_inits[j]);
+        const int k = (int)w[j].rows();
+        h[j].resize(k, n);
+        d[j].resize(k);
+        mse[j].resize(cap); ft[j].resize(cap); so[j].resize(cap); it[j].resize(cap);
+        tr[j] = sgl_trace{mse[j].data(), it[j].data(), ft[j].data(), so[j].data(), cap, 0};
+        jobs[j] = sgl_fit_job{k, 0, (uint64_t)seeds[j], w[j].data(), d[j].data(), h[j].data(), &tr[j]};
+    }
+    Progress p{false, true};
+    sgl_callbacks cb = callbacks(p);  // only poll_interrupt is used by the batch entry point
+    sgl_csc a = view(A), at = view(At);
+    check(sgl_ard_nmf_batch(handle(), &a, 1, &at, 1, tol, maxit, L1, L2, inv_density, overfit_threshold, trace_test_mse, jobs.data(),
+                            n_jobs, 0, &cb));
+    Rcpp::List out(n_jobs);
+    for (int j = 0; j < n_jobs; ++j) {
+        const int q = tr[j].length;
+        out[j] = Rcpp::List::create(Rcpp::Named("w") = w[j], Rcpp::Named("d") = d[j], Rcpp::Named("h") = h[j],
+                                    Rcpp::Named("test_mse") = Rcpp::NumericVector(mse[j].begin(), mse[j].begin() + q),
+                                    Rcpp::Named("iter") = Rcpp::IntegerVector(it[j].begin(), it[j].begin() + q),
+                                    Rcpp::Named("tol") = Rcpp::NumericVector(ft[j].begin(), ft[j].begin() + q),
+                                    Rcpp::Named("score_overfit") = Rcpp::NumericVector(so[j].begin(), so[j].begin() + q));
+    }
+    return out;
+}
