@@ -62,6 +62,8 @@ struct DevBuf {  // grow-only device scratch
 
 struct TileIndex {  // per padded rank: row tiling + the matrix re-laid out as warp streams (spmm.cuh)
     int rb_rows = 0, n_tiles = 0, nc = 0, pad = 0;
+    int32_t* perm = nullptr;  // [n_groups * nc] column held by every group slot (-1 = none); see spmm.cuh
+    bool permuted = false;
     int64_t ncol_pad = 0, n_groups = 0, stream_len = 0;
     int32_t* tileptr = nullptr;
     int64_t* goff = nullptr;
@@ -199,6 +201,7 @@ static void matrix_release(sgl_matrix* m) {
     if (m->rec) cudaFree(m->rec);
     for (auto& kv : m->tiles) {
         if (kv.second.tileptr) cudaFree(kv.second.tileptr);
+        if (kv.second.perm) cudaFree(kv.second.perm);
         if (kv.second.goff) cudaFree(kv.second.goff);
         if (kv.second.stream) cudaFree(kv.second.stream);
     }
@@ -371,7 +374,7 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
 static int fill_stream(sgl_handle* h, const sgl_matrix* m, const TileIndex& ti, const uint2* rec, uint2* st) {
     const int64_t warps = ti.n_groups * ti.n_tiles;
     if (warps > 0) {
-        stream_fill_kernel<<<blocks_for(warps, 8), 256, 0, h->stream>>>(rec, m->colptr, ti.tileptr, ti.goff, m->ncol, ti.ncol_pad,
+        stream_fill_kernel<<<blocks_for(warps, 8), 256, 0, h->stream>>>(rec, m->colptr, ti.tileptr, ti.perm, ti.goff, m->ncol, ti.ncol_pad,
                                                                      ti.n_tiles, ti.rb_rows, ti.nc, ti.pad, ti.n_groups, st);
         LAUNCH_CHECK(h);
     }
@@ -453,10 +456,48 @@ static int get_tiles(sgl_handle* h, sgl_matrix* m, int kpv, const TileIndex** ou
     DISPATCH_KP(kpv, (ti.nc = SpmmCfg<KP>::NC, ti.pad = SpmmCfg<KP>::PAD));
     ti.n_groups = (m->ncol + ti.nc - 1) / ti.nc;
     if (ti.n_groups < 1) ti.n_groups = 1;
+    // which columns form a group: identity, unless the non-zero counts are skewed enough (genes of real data) that the
+    // busiest warp would hold up its CTA -- then the columns are sorted by count and dealt to the groups in snake order
+    {
+        const int64_t slots = ti.n_groups * ti.nc;
+        std::vector<int32_t> perm((size_t)slots, -1);
+        for (int64_t c = 0; c < m->ncol; ++c) perm[(size_t)c] = (int32_t)c;
+        if (ti.n_groups >= 2 && m->ncol <= 0x7fffffffLL) {
+            std::vector<int64_t> cp((size_t)m->ncol + 1);
+            SGL_CUDA(cudaMemcpyAsync(cp.data(), m->colptr, sizeof(int64_t) * cp.size(), cudaMemcpyDeviceToHost, h->stream));
+            SGL_CUDA(cudaStreamSynchronize(h->stream));
+            int64_t worst = 0;
+            for (int64_t g = 0; g < ti.n_groups; ++g) {
+                const int64_t c0 = g * ti.nc, c1 = (c0 + ti.nc < m->ncol) ? c0 + ti.nc : m->ncol;
+                const int64_t load = cp[(size_t)c1] - cp[(size_t)c0];
+                worst = load > worst ? load : worst;
+            }
+            const double mean = (double)m->nnz / (double)ti.n_groups;
+            static const char* dbg_perm = getenv("SGL_SPMM_PERMUTE");  // debug: 0 = never, 1 = always
+            const bool want = dbg_perm ? dbg_perm[0] == '1' : (mean > 0 && (double)worst > 1.3 * mean);
+            if (want) {
+                std::vector<int32_t> order((size_t)m->ncol);
+                for (int64_t c = 0; c < m->ncol; ++c) order[(size_t)c] = (int32_t)c;
+                std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+                    return (cp[(size_t)a + 1] - cp[(size_t)a]) > (cp[(size_t)b + 1] - cp[(size_t)b]);
+                });
+                std::fill(perm.begin(), perm.end(), -1);
+                for (int64_t q = 0; q < m->ncol; ++q) {  // round r deals groups 0..G-1 (even r) or G-1..0 (odd r)
+                    const int64_t r = q / ti.n_groups, pos = q % ti.n_groups;
+                    const int64_t g = (r & 1) ? ti.n_groups - 1 - pos : pos;
+                    perm[(size_t)(g * ti.nc + r)] = order[(size_t)q];
+                }
+                ti.permuted = true;
+            }
+        }
+        SGL_CUDA(cudaMalloc(&ti.perm, sizeof(int32_t) * (size_t)(slots > 0 ? slots : 1)));
+        SGL_CUDA(cudaMemcpyAsync(ti.perm, perm.data(), sizeof(int32_t) * (size_t)slots, cudaMemcpyHostToDevice, h->stream));
+        SGL_CUDA(cudaStreamSynchronize(h->stream));  // `perm` (host) goes out of scope
+    }
     const int64_t n_off = ti.n_groups * (ti.n_tiles + 1);
     SGL_TRY(h->counts.ensure((size_t)n_off + 2));
     SGL_CUDA(cudaMalloc(&ti.goff, sizeof(int64_t) * (size_t)(n_off + 1)));
-    stream_counts_kernel<<<blocks_for(n_off, 256), 256, 0, h->stream>>>(ti.tileptr, m->ncol, ti.ncol_pad, ti.n_tiles, ti.nc, ti.pad,
+    stream_counts_kernel<<<blocks_for(n_off, 256), 256, 0, h->stream>>>(ti.tileptr, ti.perm, m->ncol, ti.ncol_pad, ti.n_tiles, ti.nc, ti.pad,
                                                                       ti.n_groups, h->counts.p);
     LAUNCH_CHECK(h);
     exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->counts.p, n_off, ti.goff);
@@ -510,7 +551,7 @@ static int launch_spmm(sgl_handle* h, const sgl_matrix* X, const uint2* stream, 
         attr_done = true;
     }
     dim3 grid(blocks_for(ti.n_groups, C::WARPS), (unsigned)splits);
-    spmm_stream_kernel<KP><<<grid, C::WARPS * 32, smem, h->stream>>>(stream, ti.goff, ti.tileptr, X->ncol, ti.ncol_pad, X->nrow,
+    spmm_stream_kernel<KP><<<grid, C::WARPS * 32, smem, h->stream>>>(stream, ti.goff, ti.tileptr, ti.perm, X->ncol, ti.ncol_pad, X->nrow,
                                                                     ti.rb_rows, ti.n_tiles, tiles_per_split, F, Bout);
     LAUNCH_CHECK(h);
     return SGL_OK;

@@ -8,7 +8,10 @@
 //     for tile t: for column j of the group: the records {int32 row, float value} of X[:, col] whose
 //     row falls in tile t, padded with {first row of tile t, 0.0f} to a multiple of PAD records.
 // goff[group][t] is the stream position of (group, t). A warp therefore reads ONE contiguous array
-// front to back: fully coalesced, no per-record predicates, and trivially prefetchable.
+// front to back: fully coalesced, no per-record predicates, and trivially prefetchable. Which columns
+// form a group is given by perm[group * NC + j] (-1 = no column): the identity for evenly filled
+// matrices, a snake deal of the columns sorted by their non-zero count when the counts are skewed
+// (genes of real data), so that the warps of a CTA -- and the CTAs -- finish together.
 //
 // Kernel. One CTA = 16 warps = 16 column groups; it walks a range of row tiles. Per tile the F tile
 // (rb_rows x KP floats, contiguous) is staged by ONE bulk async copy (TMA: cp.async.bulk -> UBLKCP)
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(SpmmCfg<KP>::WARPS * 32, 1)
 spmm_stream_kernel(const uint2* __restrict__ stream,     // warp streams (see header)
                    const int64_t* __restrict__ goff,     // [n_groups][n_tiles + 1]
                    const int32_t* __restrict__ tileptr,  // [n_tiles + 1][ncol_pad]
+                   const int32_t* __restrict__ perm,     // [n_groups * NC] column of every group slot, -1 = none
                    int64_t ncol, int64_t ncol_pad, int64_t nrow, int rb_rows, int n_tiles, int tiles_per_split,
                    const float* __restrict__ F,  // [nrow][KP]
                    float* __restrict__ Bout)     // [splits][ncol][KP]
@@ -147,8 +151,8 @@ spmm_stream_kernel(const uint2* __restrict__ stream,     // warp streams (see he
         for (int f = 0; f < C::FPL / 2; ++f) acc[j][f] = 0ull;
 
     // per-column record counts of a tile come from the tile index (lanes < NC hold one column each)
-    const int64_t my_col = col0 + lane;
-    const bool my_col_ok = (lane < C::NC) && (my_col < ncol);
+    const int64_t my_col = (lane < C::NC && group_ok) ? (int64_t)perm[col0 + lane] : -1;
+    const bool my_col_ok = my_col >= 0;
     int32_t p0 = 0, p1 = 0;  // tileptr[t], tileptr[t+1]
     if (my_col_ok && t_begin < t_end) {
         p0 = tileptr[(int64_t)t_begin * ncol_pad + my_col];
@@ -239,8 +243,8 @@ spmm_stream_kernel(const uint2* __restrict__ stream,     // warp streams (see he
             out[2 * f] = lo;
             out[2 * f + 1] = hi;
         }
-        const int64_t col = col0 + j;
-        if (g == 0 && col < ncol) {
+        const int64_t col = __shfl_sync(0xffffffffu, my_col, j);
+        if (g == 0 && col >= 0) {
             float4* dst = reinterpret_cast<float4*>(Bout + ((int64_t)blockIdx.y * ncol + col) * KP) + q;
 #pragma unroll
             for (int u = 0; u < C::NV; ++u)
@@ -276,8 +280,8 @@ __global__ void build_tileptr_kernel(const uint2* __restrict__ rec, const int64_
 
 // padded record count of every (group, tile), flattened as [n_groups][n_tiles + 1] with a zero in the
 // last slot of each row: the exclusive scan of this array is goff.
-__global__ void stream_counts_kernel(const int32_t* __restrict__ tileptr, int64_t ncol, int64_t ncol_pad, int n_tiles,
-                                     int nc, int pad, int64_t n_groups, int64_t* __restrict__ counts) {
+__global__ void stream_counts_kernel(const int32_t* __restrict__ tileptr, const int32_t* __restrict__ perm, int64_t ncol,
+                                     int64_t ncol_pad, int n_tiles, int nc, int pad, int64_t n_groups, int64_t* __restrict__ counts) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_groups * (n_tiles + 1)) return;
     const int64_t grp = e / (n_tiles + 1);
@@ -285,8 +289,8 @@ __global__ void stream_counts_kernel(const int32_t* __restrict__ tileptr, int64_
     int64_t tot = 0;
     if (t < n_tiles) {
         for (int j = 0; j < nc; ++j) {
-            const int64_t col = grp * nc + j;
-            if (col < ncol) {
+            const int64_t col = perm[grp * nc + j];
+            if (col >= 0) {
                 const int32_t n = tileptr[(int64_t)(t + 1) * ncol_pad + col] - tileptr[(int64_t)t * ncol_pad + col];
                 tot += (n + pad - 1) / pad * pad;
             }
@@ -298,7 +302,7 @@ __global__ void stream_counts_kernel(const int32_t* __restrict__ tileptr, int64_
 // fill the warp streams from column-compressed records: one warp per (group, tile)
 __global__ void __launch_bounds__(256)
 stream_fill_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ colptr, const int32_t* __restrict__ tileptr,
-                   const int64_t* __restrict__ goff, int64_t ncol, int64_t ncol_pad, int n_tiles, int rb_rows, int nc, int pad,
+                   const int32_t* __restrict__ perm, const int64_t* __restrict__ goff, int64_t ncol, int64_t ncol_pad, int n_tiles, int rb_rows, int nc, int pad,
                    int64_t n_groups, uint2* __restrict__ stream) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -308,8 +312,8 @@ stream_fill_kernel(const uint2* __restrict__ rec, const int64_t* __restrict__ co
     int64_t dst = goff[grp * (n_tiles + 1) + t];
     const uint2 padrec = make_uint2((uint32_t)(t * rb_rows), 0u);
     for (int j = 0; j < nc; ++j) {
-        const int64_t col = grp * nc + j;
-        if (col >= ncol) break;
+        const int64_t col = perm[grp * nc + j];
+        if (col < 0) continue;
         const int32_t b = tileptr[(int64_t)t * ncol_pad + col], e = tileptr[(int64_t)(t + 1) * ncol_pad + col];
         const int32_t n = e - b, np = (n + pad - 1) / pad * pad;
         const uint2* src = rec + colptr[col] + b;
