@@ -117,3 +117,37 @@ def test_distributed_transpose_blocks():
     import scipy.sparse as sp
 
     assert (sp.hstack(blocks).tocsc() != A.T.tocsc()).nnz == 0
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors of the C-ABI structs (sgl_csc, sgl_callbacks, sgl_trace, sgl_fit_job) have the size and field
+    offsets a C compiler gives the declarations in include/singlet_cuda.h (the header is compiled as plain C here)."""
+    import ctypes as C
+    import subprocess
+
+    from singlet_b200 import _lib
+
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    structs = {"sgl_csc": (_lib.Csc, ["nrow", "ncol", "p", "i", "x"]),
+               "sgl_callbacks": (_lib.Callbacks, ["user", "poll_interrupt", "on_iter"]),
+               "sgl_trace": (_lib.Trace, ["test_mse", "iter", "tol", "score_overfit", "capacity", "length"]),
+               "sgl_fit_job": (_lib.FitJob, ["k", "status", "seed", "w", "d", "h", "trace"])}
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "singlet_cuda.h"', "int main(void) {"]
+    for name, (_, fields) in structs.items():
+        src.append(f'  printf("{name} %zu", sizeof({name}));')
+        for f in fields:
+            src.append(f'  printf(" %zu", offsetof({name}, {f}));')
+        src.append('  printf("\\n");')
+    src += ["  return 0;", "}"]
+    c_file, exe = tmp_path / "abi.c", tmp_path / "abi"
+    c_file.write_text("\n".join(src))
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(c_file), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = {}
+    for line in out:
+        if line.strip():
+            parts = line.split()
+            seen[parts[0]] = [int(v) for v in parts[1:]]
+    for name, (cls, fields) in structs.items():
+        exp = [C.sizeof(cls)] + [getattr(cls, f).offset for f in fields]
+        assert seen[name] == exp, (name, seen[name], exp)
