@@ -44,6 +44,11 @@ class OracleBackend:
     def upload(self, A):
         return A.tocsc()
 
+    def transpose(self, X):
+        T = X.T.tocsc()
+        T.sort_indices()
+        return T
+
     def mask_build(self, X, seed, inv_density, mask_t, col_offset, row_offset):
         return (seed, inv_density, mask_t, col_offset, row_offset)
 
@@ -158,8 +163,9 @@ def _worker(rank, world, port, q):
         cv = sharded_ard_nmf(be, m, n, k, A[:, c0:c1].tocsc(), At[:, g0:g1].tocsc(), w0, 123, 5, tol=0.0, maxit=3,
                              overfit_threshold=10.0, trace_test_mse=2, rank=rank, world=world)
         # layout B: the rank's transpose block covers its own cells only
-        resb = sharded_nmf(be, m, n, k, A[:, c0:c1].tocsc(), A[:, c0:c1].T.tocsc(), w0, tol=0.0, maxit=4, L1=(0.01, 0.02),
-                           rank=rank, world=world, layout="B")
+        # (rank 0 hands it over, rank 1 lets the driver derive it from its cell block: At_shard = None)
+        resb = sharded_nmf(be, m, n, k, A[:, c0:c1].tocsc(), A[:, c0:c1].T.tocsc() if rank == 0 else None, w0, tol=0.0, maxit=4,
+                           L1=(0.01, 0.02), rank=rank, world=world, layout="B")
         q.put((rank, res["w"], res["h"], res["d"], res["tol"], cv["test_mse"], cv["h"], resb["w"], resb["h"], resb["d"]))
     finally:
         dist.destroy_process_group()
