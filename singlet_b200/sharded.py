@@ -401,3 +401,51 @@ def sharded_ard_nmf(backend, m, n, k, A_shard, At_shard, w_init, seed, inv_densi
     w, d, h = fit.factors_to_host()
     return {"w": w, "d": d, "h": h, "test_mse": np.array(test_mse), "iter": np.array(iters, np.int32), "tol": np.array(tols),
             "score_overfit": np.array(scores)}
+
+
+def distributed_cross_validate_nmf(A, ranks, n_replicates=3, tol=1e-4, maxit=100, L1=0.01, L2=0, test_density=0.05,
+                                   tol_overfit=1e-4, trace_test_mse=5, seed=None, device=None, group=None, concurrency=0, handle=None):
+    """``cross_validate_nmf`` (reference R/cross_validate_nmf.R:18-105) with the (rank, replicate) grid dealt over the
+    processes of ``group`` (one process per GPU): the fits are independent, so every process uploads A, runs its share
+    with ``sgl_ard_nmf_batch`` and the traces are gathered -- no data-path collective ("replicas" of the CV path, SURVEY.md
+    8e). Every process returns the same DataFrame, identical to ``api.cross_validate_nmf`` on one GPU. ``seed``: R's
+    ``set.seed`` value (all processes must draw the same w_init and mask seeds)."""
+    import pandas as pd
+
+    from . import api
+    from .rrng import RRng
+
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    r = RRng(0)
+    r.set_seed(123 if seed is None else seed)
+    ranks = [int(k) for k in np.atleast_1d(ranks)]
+    A = api._as_csc(A)
+    m = A.shape[0]
+    w_init = [r.matrix_runif(max(ranks), m) for _ in range(n_replicates)]
+    grid = [(k, rep) for rep in range(1, n_replicates + 1) for k in ranks]
+    seeds = [abs(r.dot_random_seed(3 + rep)) for _, rep in grid]
+    # largest ranks first, dealt round-robin: every process gets a similar mix of long and short fits
+    order = sorted(range(len(grid)), key=lambda j: -grid[j][0])
+    mine = order[rank::world]
+    own = handle is None
+    if own:
+        handle = api.Handle(device if device is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0))
+    try:
+        models = api.c_ard_nmf_batch(A, None, tol, maxit, L1, L2, 0, [w_init[grid[j][1] - 1][:grid[j][0], :] for j in mine],
+                                     [seeds[j] for j in mine], int(round(1 / test_density)), tol_overfit, trace_test_mse,
+                                     concurrency, handle) if mine else []
+    finally:
+        if own:
+            handle.close()
+    part = {j: (mod["test_mse"], mod["iter"], mod["tol"]) for j, mod in zip(mine, models)}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, part, group=group)
+        part = {j: v for g in gathered for j, v in g.items()}
+    rows = []
+    for j, (k, rep) in enumerate(grid):
+        mse, it, ft = part[j]
+        for q in range(len(mse)):
+            rows.append({"k": k, "rep": rep, "test_error": mse[q], "iter": int(it[q]), "tol": ft[q]})
+    return pd.DataFrame(rows, columns=["k", "rep", "test_error", "iter", "tol"])
