@@ -209,3 +209,76 @@ def test_shard_bounds_cover_everything():
                 assert lo == min(r * per, total) and lo <= hi <= total
                 seen += hi - lo
             assert seen == total
+
+
+def _fake_batch(orc):
+    """Stand-in for api.c_ard_nmf_batch on a machine without a GPU: the oracle, fit by fit."""
+    def batch(A, At, tol, maxit, L1, L2, threads, ws, seeds, inv_density, overfit_threshold, trace_test_mse, concurrency=0, handle=None):
+        At = A.T.tocsc()
+        return [orc.ard_nmf(A, At, w, s, inv_density, tol=tol, maxit=maxit, L1=L1, L2=L2, overfit_threshold=overfit_threshold,
+                            trace_test_mse=trace_test_mse) for w, s in zip(ws, seeds)]
+    return batch
+
+
+def _cv_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.pyoracle import Oracle
+        from singlet_b200 import api, sharded, synth
+
+        class NoHandle:
+            def close(self):
+                pass
+
+        calls = []
+        fake = _fake_batch(Oracle("port"))
+
+        def counting(*a, **kw):
+            calls.append(len(a[7]))
+            return fake(*a, **kw)
+
+        api.c_ard_nmf_batch, api.Handle = counting, (lambda *a, **kw: NoHandle())
+        A = synth.synth_scipy(60, 45, 0.25, seed=9)
+        df = sharded.distributed_cross_validate_nmf(A, [2, 3, 5, 4], n_replicates=2, maxit=6, trace_test_mse=2, seed=77, device=0)
+        q.put((rank, df.to_dict("list"), calls))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cv_sweep_dealt_over_two_ranks_equals_the_sequential_sweep(oracle):
+    """distributed_cross_validate_nmf: the (rank, replicate) grid is dealt over the processes and gathered; every process
+    ends with the data frame of the sequential sweep (R/cross_validate_nmf.R:69-97), rows in expand.grid order."""
+    from singlet_b200 import api, synth
+    from singlet_b200.rrng import RRng
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_cv_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # sequential expectation with the same R RNG stream
+    A = synth.synth_scipy(60, 45, 0.25, seed=9)
+    At = A.T.tocsc()
+    r = RRng(0)
+    r.set_seed(77)
+    ks = [2, 3, 5, 4]
+    w_init = [r.matrix_runif(max(ks), 60) for _ in range(2)]
+    exp = {"k": [], "rep": [], "test_error": [], "iter": [], "tol": []}
+    for rep in (1, 2):
+        for k in ks:
+            mod = oracle.ard_nmf(A, At, w_init[rep - 1][:k, :], abs(r.dot_random_seed(3 + rep)), 20, tol=1e-4, maxit=6, L1=0.01, L2=0.0,
+                                 overfit_threshold=1e-4, trace_test_mse=2)
+            for t in range(len(mod["test_mse"])):
+                exp["k"].append(k); exp["rep"].append(rep); exp["test_error"].append(float(mod["test_mse"][t]))
+                exp["iter"].append(int(mod["iter"][t])); exp["tol"].append(float(mod["tol"][t]))
+    assert sorted(outs[0][2] + outs[1][2]) == [4, 4]  # eight fits, four per process
+    for _, got, _ in outs:
+        assert got["k"] == exp["k"] and got["rep"] == exp["rep"] and got["iter"] == exp["iter"]
+        assert np.allclose(got["test_error"], exp["test_error"], rtol=1e-12) and np.allclose(got["tol"], exp["tol"], rtol=1e-12)
