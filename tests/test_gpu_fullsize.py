@@ -93,3 +93,28 @@ def test_mask_consistent_between_orientations(big):
     be.lib.sgl_mask_info(mAt, C.byref(c), C.byref(d))
     assert a.value == c.value and b.value == d.value  # same held-out set seen from cells and from genes
     assert abs(a.value / (M * N) - 0.05) < 2e-4 and abs(b.value / be.matrix_info(A)[2] - 0.05) < 5e-4
+
+
+def test_device_transpose_at_full_size(big):
+    """sgl_matrix_transpose of the 1.5 G non-zero matrix: the transpose built on the device is indistinguishable from the
+    independently GENERATED At -- same column counts, and bit-identical right-hand-side products for a random factor
+    (every column sum is formed in row order, so any misplaced, missing or reordered record would change bits) -- and
+    transposing twice gives back A in the same sense."""
+    be, A, At = big
+    T = be.transpose(A)
+    assert be.matrix_info(T) == be.matrix_info(At)
+    assert torch.equal(be.column_counts(T), be.column_counts(At))
+    g = torch.Generator(device="cpu").manual_seed(7)
+    kp = be.kp(K)
+    F = torch.rand((N, kp), generator=g).to(be.device)
+    B1, B2 = be.zeros_factor(M, K), be.zeros_factor(M, K)
+    be.rhs(At, F, K, B1)
+    be.rhs(T, F, K, B2)
+    assert torch.equal(B1, B2)
+    TT = be.transpose(T)
+    assert be.matrix_info(TT) == be.matrix_info(A) and torch.equal(be.column_counts(TT), be.column_counts(A))
+    Fm = torch.rand((M, kp), generator=g).to(be.device)
+    C1, C2 = be.zeros_factor(N, K), be.zeros_factor(N, K)
+    be.rhs(A, Fm, K, C1)
+    be.rhs(TT, Fm, K, C2)
+    assert torch.equal(C1, C2)
