@@ -93,6 +93,11 @@ class CudaBackend:
         self._mats.append(m)
         return m
 
+    def free_matrix(self, mat):
+        """Release a device matrix now (close() releases whatever is left)."""
+        self._mats = [m for m in self._mats if m.value != mat.value]
+        _lib.check(self.lib.sgl_matrix_free(self._h, mat))
+
     def synth(self, m_genes, n_cells, density, seed, orientation, col0, ncol, table):
         table = np.ascontiguousarray(table, dtype=np.float32)
         m = C.c_void_p()

@@ -84,17 +84,6 @@ def test_one_iteration_invariants(big):
     assert float(fit.d[:K].min()) > 0.0
 
 
-def test_mask_consistent_between_orientations(big):
-    be, A, At = big
-    mA = be.mask_build(A, 123, 20, 0, 0, 0)
-    mAt = be.mask_build(At, 123, 20, 1, 0, 0)
-    a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
-    be.lib.sgl_mask_info(mA, C.byref(a), C.byref(b))
-    be.lib.sgl_mask_info(mAt, C.byref(c), C.byref(d))
-    assert a.value == c.value and b.value == d.value  # same held-out set seen from cells and from genes
-    assert abs(a.value / (M * N) - 0.05) < 2e-4 and abs(b.value / be.matrix_info(A)[2] - 0.05) < 5e-4
-
-
 def test_device_transpose_at_full_size(big):
     """sgl_matrix_transpose of the 1.5 G non-zero matrix: the transpose built on the device is indistinguishable from the
     independently GENERATED At -- same column counts, and bit-identical right-hand-side products for a random factor
@@ -118,3 +107,17 @@ def test_device_transpose_at_full_size(big):
     be.rhs(A, Fm, K, C1)
     be.rhs(TT, Fm, K, C2)
     assert torch.equal(C1, C2)
+    be.free_matrix(T)
+    be.free_matrix(TT)
+
+
+def test_mask_consistent_between_orientations(big):
+    be, A, At = big
+    mA = be.mask_build(A, 123, 20, 0, 0, 0)
+    mAt = be.mask_build(At, 123, 20, 1, 0, 0)
+    a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    be.lib.sgl_mask_info(mA, C.byref(a), C.byref(b))
+    be.lib.sgl_mask_info(mAt, C.byref(c), C.byref(d))
+    assert a.value == c.value and b.value == d.value  # same held-out set seen from cells and from genes
+    assert abs(a.value / (M * N) - 0.05) < 2e-4 and abs(b.value / be.matrix_info(A)[2] - 0.05) < 5e-4
+
