@@ -624,7 +624,22 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
     LAUNCH_CHECK(h);
     ProfScope ps_nnls(h, PK_NNLS, 0);
     int64_t n_parts = 0;
-    if (!mask) {
+    if (!mask && KPV >= 16 && KPV <= 32 && ncol < 20000) {
+        // few columns: the thread-per-column kernel would be latency-bound (one warp per SM); the sub-warp kernel with no
+        // held-out lists is the same solve with 4-8 lanes per column and a blocked sweep (nnls.cuh)
+        int G = 1;
+        DISPATCH_KP(KPV, G = (KP <= 32) ? MaskedSubCfg<(KP <= 32 ? KP : 32)>::G : 1);
+        const int64_t n_groups = (ncol + G - 1) / G;
+        n_parts = (n_groups + 3) / 4;
+        SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
+        if (KPV == 16)
+            nnls_masked_sub_kernel<16, 1><<<(unsigned)n_parts, 128, 0, h->stream>>>(Bparts, splits, F_out, h->gram_f.p, F_in, colptr, nullptr,
+                                                                                  nullptr, ncol, k, (float)L1, (float)L2, h->part.p);
+        else
+            nnls_masked_sub_kernel<32, 1><<<(unsigned)n_parts, 128, 0, h->stream>>>(Bparts, splits, F_out, h->gram_f.p, F_in, colptr, nullptr,
+                                                                                  nullptr, ncol, k, (float)L1, (float)L2, h->part.p);
+        LAUNCH_CHECK(h);
+    } else if (!mask) {
         if (KPV <= 64) {
             // persistent grid: every SM gets as many CTAs as fit, each lane claims columns from a counter
             static const bool dbg_stats = getenv("SGL_NNLS_STATS") != nullptr;

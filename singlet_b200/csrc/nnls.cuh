@@ -436,6 +436,10 @@ nnls_masked_kernel(const float* __restrict__ Bparts, int splits, float* __restri
 // accumulates the correction over its share of the held-out rows and warp 0 folds the partial sums
 // through shared memory before solving. The host picks the largest WS whose grid is still resident
 // in one wave.
+// The same kernel with mptr == nullptr (no held-out lists, a_i = the Gram) is the PLAIN solver for small column
+// counts (a gene shard of the W update on 8 GPUs, pbmc3k): there the thread-per-column kernel has one warp per SM and
+// is bound by the latency of its per-coordinate chain (~150 cycles x 3200 steps), while four (eight) lanes per column with
+// the blocked sweep need ~100 cycles per block of four coordinates.
 #ifndef SGL_MASKED32_MINB
 #define SGL_MASKED32_MINB 3
 #endif
@@ -482,7 +486,7 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
         for (int i = 0; i < KP; ++i) a[c][i] = 0.f;
     int64_t mb = 0;
     int my_n = 0;  // my share: held-out entries mb + wsub + WS * t, t < my_n
-    if (solve) {
+    if (solve && mptr) {  // mptr == nullptr: no mask at all (plain solve of a few columns, see below)
         mb = mptr[col];
         const int64_t len = mptr[col + 1] - mb;
         my_n = (int)((len - wsub + WS - 1) / WS);
@@ -518,15 +522,17 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
         for (int q = 0; q < CPL; ++q)
             cp_async16(ring + (uint32_t)stage * STAGE_BYTES + (uint32_t)(lane * CPL + q) * 16u, src + 4 * q, ok ? 16u : 0u);
     };
-    copy_idx(0);
-    copy_idx(1);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncwarp();
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-        issue(d, d);
+    if (max_n > 0) {  // warp-uniform
+        copy_idx(0);
+        copy_idx(1);
         cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            issue(d, d);
+            cp_async_commit();
+        }
     }
     for (int tb = 0; tb < max_n; tb += D) {
 #pragma unroll
