@@ -151,3 +151,15 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     for name, (cls, fields) in structs.items():
         exp = [C.sizeof(cls)] + [getattr(cls, f).offset for f in fields]
         assert seen[name] == exp, (name, seen[name], exp)
+
+
+def test_rcpp_glue_type_checks_against_the_c_header():
+    """rglue/singlet_cuda_glue.cpp (the bodies a maintainer drops into the R package) cannot be built here (no R), but it
+    is type-checked against include/singlet_cuda.h with minimal stand-ins for Rcpp / RcppEigen (tests/rglue_stub): every
+    sgl_* call in the glue matches the declared signature."""
+    import subprocess
+
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(root, "tests", "rglue_stub"), "-I",
+                        os.path.join(root, "include"), os.path.join(root, "rglue", "singlet_cuda_glue.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
