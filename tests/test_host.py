@@ -163,3 +163,35 @@ def test_rcpp_glue_type_checks_against_the_c_header():
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(root, "tests", "rglue_stub"), "-I",
                         os.path.join(root, "include"), os.path.join(root, "rglue", "singlet_cuda_glue.cpp")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_cross_validate_nmf_host_logic_batch_equals_fit_by_fit(monkeypatch):
+    """Host side of cross_validate_nmf (reference R/cross_validate_nmf.R:57-105) without a GPU: with the fits replaced by
+    the CPU oracle, the batched grid (one c_ard_nmf_batch call) and the fit-by-fit loop draw the same w_init slices and
+    mask seeds from R's RNG stream and build the same data frame, in expand.grid order."""
+    from oracle.pyoracle import Oracle
+    from singlet_b200 import api, synth
+
+    orc = Oracle("port")
+    seen = {"batch": [], "loop": []}
+
+    def fake_fit(A, At, tol, maxit, verbose, L1, L2, threads, w, seed, inv_density, thr, trace, handle=None):
+        seen["loop"].append((w.shape[0], int(seed)))
+        return orc.ard_nmf(A, A.T.tocsc(), w, seed, inv_density, tol=tol, maxit=maxit, L1=L1, L2=L2, overfit_threshold=thr, trace_test_mse=trace)
+
+    def fake_batch(A, At, tol, maxit, L1, L2, threads, ws, seeds, inv_density, thr, trace, concurrency=0, handle=None):
+        seen["batch"] += [(w.shape[0], int(s)) for w, s in zip(ws, seeds)]
+        return [orc.ard_nmf(A, A.T.tocsc(), w, s, inv_density, tol=tol, maxit=maxit, L1=L1, L2=L2, overfit_threshold=thr, trace_test_mse=trace)
+                for w, s in zip(ws, seeds)]
+
+    monkeypatch.setattr(api, "c_ard_nmf", fake_fit)
+    monkeypatch.setattr(api, "c_ard_nmf_batch", fake_batch)
+    A = synth.synth_scipy(50, 40, 0.3, seed=4)
+    api.set_seed(11)
+    df_b = api.cross_validate_nmf(A, [2, 4, 3], n_replicates=2, maxit=5, verbose=0, batch=True)
+    api.set_seed(11)
+    df_l = api.cross_validate_nmf(A, [2, 4, 3], n_replicates=2, maxit=5, verbose=0, batch=False)
+    assert df_b.equals(df_l) and len(df_b) > 0
+    assert seen["batch"] == seen["loop"] and [k for k, _ in seen["loop"]] == [2, 4, 3, 2, 4, 3]
+    assert len({s for _, s in seen["loop"][:3]}) == 1 and seen["loop"][0][1] != seen["loop"][3][1]  # one mask seed per replicate
+    assert list(df_b["k"].unique()) == [2, 4, 3] and list(df_b["rep"].unique()) == [1, 2]
