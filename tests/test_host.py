@@ -195,3 +195,52 @@ def test_cross_validate_nmf_host_logic_batch_equals_fit_by_fit(monkeypatch):
     assert seen["batch"] == seen["loop"] and [k for k, _ in seen["loop"]] == [2, 4, 3, 2, 4, 3]
     assert len({s for _, s in seen["loop"][:3]}) == 1 and seen["loop"][0][1] != seen["loop"][3][1]  # one mask seed per replicate
     assert list(df_b["k"].unique()) == [2, 4, 3] and list(df_b["rep"].unique()) == [1, 2]
+
+
+def test_ard_nmf_rank_search_host_logic(monkeypatch):
+    """Host side of ard_nmf (reference R/ard_nmf.R:95-178) without a GPU, fits replaced by the CPU oracle on a matrix with
+    three planted factors: the search starts at k_init, never leaves [k_min, k_max], never repeats a rank within a
+    replicate, uses the mask seed test_seed + rep, and the final unmasked fit runs at GetBestRank of the table with the
+    first best_rank rows of the first w_init."""
+    import scipy.sparse as sp
+
+    from oracle.pyoracle import Oracle
+    from singlet_b200 import api
+
+    orc = Oracle("port")
+    rs = np.random.RandomState(0)
+    Wt = rs.gamma(1.0, 1.0, size=(80, 3)) * (rs.uniform(size=(80, 3)) < 0.4)
+    Ht = rs.gamma(1.0, 1.0, size=(3, 70)) * (rs.uniform(size=(3, 70)) < 0.5)
+    D = Wt @ Ht + 0.01 * rs.uniform(size=(80, 70)) * (rs.uniform(size=(80, 70)) < 0.3)
+    A = sp.csc_matrix(D)
+    calls, final = [], {}
+
+    def fake_fit(A_, At, tol, maxit, verbose, L1, L2, threads, w, seed, inv_density, thr, trace, handle=None):
+        calls.append((w.shape[0], int(seed)))
+        return orc.ard_nmf(A_, A_.T.tocsc(), w, seed, inv_density, tol=tol, maxit=maxit, L1=L1, L2=L2, overfit_threshold=thr, trace_test_mse=trace)
+
+    def fake_nmf(A_, At, tol, maxit, verbose, L1_w, L1_h, L2_w, L2_h, threads, w, handle=None):
+        final["k"], final["w0"] = w.shape[0], np.array(w)
+        return orc.nmf(A_, A_.T.tocsc(), w, tol=tol, maxit=maxit, L1=(L1_w, L1_h), L2=(L2_w, L2_h))
+
+    monkeypatch.setattr(api, "c_ard_nmf", fake_fit)
+    monkeypatch.setattr(api, "c_nmf", fake_nmf)
+    api.set_seed(5)
+    model = api.ard_nmf(A, k_init=2, k_max=12, n_replicates=2, maxit=30, verbose=0, tol_overfit=0.3)
+    from singlet_b200.rrng import RRng
+
+    r = RRng(0)
+    r.set_seed(5)
+    w_init = [r.matrix_runif(12, 80) for _ in range(2)]
+    test_seed = abs(r.dot_random_seed(3))
+    reps = [[k for k, s in calls if s == test_seed + rep] for rep in (1, 2)]
+    assert sum(len(x) for x in reps) == len(calls)            # every fit used test_seed + rep
+    for ks in reps:
+        assert ks[0] == 2 and len(set(ks)) == len(ks) and all(2 <= k <= 12 for k in ks)
+        assert len(ks) == 1 or ks[1] == 4                    # the step doubles while the largest rank is the best one
+    df = model["cv_data"]
+    assert list(df.columns) == ["k", "rep", "test_error", "iter", "tol", "overfit_score"]
+    best = api.GetBestRank(df, 0.3)
+    assert final["k"] == best == model["w"].shape[1] and np.array_equal(final["w0"], w_init[0][:best, :])
+    assert 2 <= best <= 12 and np.all(np.diff(model["d"]) <= 0)
+    assert len(calls) >= 3                                   # the search did move
