@@ -545,7 +545,8 @@ static int launch_spmm(sgl_handle* h, const sgl_matrix* X, const uint2* stream, 
                        float* Bout, int splits, int tiles_per_split) {
     using C = SpmmCfg<KP>;
     const size_t smem = 2 * (size_t)ti.rb_rows * KP * sizeof(float) + C::RING_BYTES + 2 * sizeof(uint64_t);
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};  // function attributes are per device
+    bool& attr_done = attr_done_dev[h->device & 63];
     if (!attr_done) {
         SGL_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
@@ -741,7 +742,8 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
             n_parts = ncol;
             SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
             const size_t smem = ((size_t)KPV * (KPV + 1) + 3 * (size_t)KPV) * sizeof(float);
-            static bool attr_done = false;
+            static bool attr_done_dev[64] = {};
+            bool& attr_done = attr_done_dev[h->device & 63];
             if (!attr_done) {
                 SGL_CUDA(cudaFuncSetAttribute(nnls_masked_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                 attr_done = true;
@@ -1006,7 +1008,8 @@ static int transpose_on_device(sgl_handle* h, const sgl_matrix* X, sgl_matrix** 
         }
         if ((rc = h->counts.ensure((size_t)X->nrow + 2)) != SGL_OK) break;
         const size_t smem = sizeof(int32_t) * (size_t)(pass_rows > 0 ? pass_rows : 1);
-        static bool attr_done = false;
+        static bool attr_done_dev[64] = {};
+        bool& attr_done = attr_done_dev[h->device & 63];
         if (!attr_done) {
             cudaFuncSetAttribute(transpose_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             cudaFuncSetAttribute(transpose_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
