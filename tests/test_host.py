@@ -244,3 +244,33 @@ def test_ard_nmf_rank_search_host_logic(monkeypatch):
     assert final["k"] == best == model["w"].shape[1] and np.array_equal(final["w0"], w_init[0][:best, :])
     assert 2 <= best <= 12 and np.all(np.diff(model["d"]) <= 0)
     assert len(calls) >= 3                                   # the search did move
+
+
+def test_run_nmf_host_logic(monkeypatch):
+    """Host side of run_nmf (reference R/run_nmf.R:39-75) without a GPU, the fit
+    replaced by the CPU oracle: w_init is the first rank * m draws of runif after set.seed (k x m, column-major fill), the
+    model comes back sorted by decreasing d with w transposed to m x k, and L1 / L2 pairs are passed through as (w, h)."""
+    from oracle.pyoracle import Oracle
+    from singlet_b200 import api, synth
+    from singlet_b200.rrng import RRng
+
+    orc = Oracle("port")
+    got = {}
+
+    def fake_nmf(A_, At, tol, maxit, verbose, L1_w, L1_h, L2_w, L2_h, threads, w, handle=None):
+        got.update(w0=np.array(w), L1=(L1_w, L1_h), L2=(L2_w, L2_h), At=At)
+        return orc.nmf(A_, A_.T.tocsc(), w, tol=tol, maxit=maxit, L1=(L1_w, L1_h), L2=(L2_w, L2_h))
+
+    monkeypatch.setattr(api, "c_nmf", fake_nmf)
+    A = synth.synth_scipy(60, 50, 0.3, seed=2)
+    api.set_seed(99)
+    model = api.run_nmf(A, 4, maxit=8, verbose=False, L1=(0.02, 0.03), L2=0.1)
+    assert np.array_equal(got["w0"], RRng(99).matrix_runif(4, 60)) and got["L1"] == (0.02, 0.03) and got["L2"] == (0.1, 0.1)
+    assert got["At"] is None                                  # the transpose is left to the device by default
+    assert model["w"].shape == (60, 4) and model["h"].shape == (4, 50) and np.all(np.diff(model["d"]) <= 0)
+    ref = orc.nmf(A, A.T.tocsc(), got["w0"], tol=1e-4, maxit=8, L1=(0.02, 0.03), L2=(0.1, 0.1))
+    order = np.argsort(-ref["d"], kind="stable")
+    assert np.allclose(model["w"], ref["w"][order].T) and np.allclose(model["h"], ref["h"][order]) and np.allclose(model["d"], ref["d"][order])
+    api.set_seed(99)
+    api.run_nmf(A, 4, maxit=2, verbose=False, device_transpose=False)
+    assert got["At"] is not None and (got["At"] != A.T.tocsc()).nnz == 0
