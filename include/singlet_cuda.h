@@ -75,6 +75,17 @@ int sgl_destroy(sgl_handle* h);
 /* Keep uploaded A/At (and the materialised mask) between calls when the same host buffers are
  * passed again (a CV sweep makes dozens of calls on one matrix). Default on. */
 int sgl_set_cache(sgl_handle* h, int enabled);
+/* Operand precision of the sparse product b = sum v * F[r, :] (src/singlet.cpp:341-343). Accumulation is FP32 in both
+ * modes, the non-zero values v stay FP32, the solver, Gram, scale, cor and loss kernels are unaffected.
+ *   SGL_PRECISION_MIXED16 (default): for padded ranks >= 32 the gathered factor F is staged as FP16 scaled by a power
+ *       of two taken from max |F| (relative rounding 2^-12 per element, averaged over the non-zeros of a column);
+ *       this halves the shared-memory gather that bounds the kernel.
+ *   SGL_PRECISION_FP32: F is gathered in FP32 (the round-1 kernel).
+ * The environment variable SGL_PRECISION=fp32 selects the FP32 mode for handles created afterwards. */
+#define SGL_PRECISION_MIXED16 0
+#define SGL_PRECISION_FP32 1
+int sgl_set_precision(sgl_handle* h, int mode);
+int sgl_get_precision(sgl_handle* h);
 int sgl_synchronize(sgl_handle* h);
 /* the cudaStream_t all work of this handle is enqueued on */
 void* sgl_stream(sgl_handle* h);

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsinglet_cuda.so")
 
 SGL_OK, SGL_EINVAL, SGL_ENODEVICE, SGL_ECUDA, SGL_EINTERRUPT, SGL_ENOMEM = 0, -1, -2, -3, -4, -5
 MAX_RANK = 128
+PRECISION_MIXED16, PRECISION_FP32 = 0, 1
 
 
 class SingletCudaError(RuntimeError):
@@ -58,6 +59,8 @@ SYMBOLS = [
     ("sgl_create", _i32, [_i32, _vp, C.POINTER(_vp)]),
     ("sgl_destroy", _i32, [_vp]),
     ("sgl_set_cache", _i32, [_vp, _i32]),
+    ("sgl_set_precision", _i32, [_vp, _i32]),
+    ("sgl_get_precision", _i32, [_vp]),
     ("sgl_synchronize", _i32, [_vp]),
     ("sgl_stream", _vp, [_vp]),
     ("sgl_launch_count", _i64, [_vp]),

@@ -60,6 +60,11 @@ class Handle:
     def launch_count(self) -> int:
         return int(self.lib.sgl_launch_count(self._h))
 
+    def set_precision(self, mode):
+        """``"mixed16"`` (default: FP16-staged gather operand, FP32 accumulation) or ``"fp32"`` (sgl_set_precision)."""
+        code = {"mixed16": _lib.PRECISION_MIXED16, "fp32": _lib.PRECISION_FP32}.get(mode, mode)
+        _lib.check(self.lib.sgl_set_precision(self._h, int(code)))
+
     def set_cache(self, enabled: bool):
         _lib.check(self.lib.sgl_set_cache(self._h, int(bool(enabled))))
 
@@ -187,7 +192,7 @@ def c_nmf(A, At, tol, maxit, verbose, L1_w, L1_h, L2_w, L2_h, threads, w, handle
 
 def c_nmf_sparse_list(A_, At_, tol, maxit, verbose, L1, L2, threads, w, handle: Handle | None = None):
     """``c_nmf_sparse_list`` (reference src/singlet.cpp:715-743): one L1/L2 for both factors."""
-    return c_nmf(list(A_), list(At_), tol, maxit, verbose, L1, L1, L2, L2, threads, w, handle)
+    return c_nmf(list(A_), None if At_ is None else list(At_), tol, maxit, verbose, L1, L1, L2, L2, threads, w, handle)
 
 
 def c_nmf_dense(A, At, tol, maxit, verbose, L1_w, L1_h, L2_w, L2_h, threads, w, handle: Handle | None = None):
@@ -337,7 +342,8 @@ def c_ard_nmf_batch(A, At, tol, maxit, L1, L2, threads, ws, seeds, inv_density, 
 def c_ard_nmf_sparse_list(A_, At_, tol, maxit, verbose, L1, L2, threads, w, rng_seed, inv_density, overfit_threshold,
                           trace_test_mse, handle: Handle | None = None):
     """``c_ard_nmf_sparse_list`` (reference src/singlet.cpp:1162-1234)."""
-    return c_ard_nmf(list(A_), list(At_), tol, maxit, verbose, L1, L2, threads, w, rng_seed, inv_density, overfit_threshold,
+    return c_ard_nmf(list(A_), None if At_ is None else list(At_), tol, maxit, verbose, L1, L2, threads, w, rng_seed, inv_density,
+                     overfit_threshold,
                      trace_test_mse, handle)
 
 

@@ -22,6 +22,7 @@
 #include "misc.cuh"
 #include "nnls.cuh"
 #include "spmm.cuh"
+#include "spmm_h16.cuh"
 
 namespace sgl {
 
@@ -60,8 +61,11 @@ struct DevBuf {  // grow-only device scratch
     }
 };
 
-struct TileIndex {  // per padded rank: row tiling + the matrix re-laid out as warp streams (spmm.cuh)
+struct TileIndex {  // per padded rank: row tiling + the matrix re-laid out as warp streams (spmm.cuh / spmm_h16.cuh)
     int rb_rows = 0, n_tiles = 0, nc = 0, pad = 0;
+    bool h16 = false;  // stream in the 16-bit-operand format (tile-relative byte offsets, alternating row parity)
+    int row_bytes = 0; // bytes of one staged operand row
+    float vscale = 1.f, inv_vscale = 1.f;  // h16: power-of-two scale of the FP16 record values and its inverse
     int32_t* perm = nullptr;  // [n_groups * nc] column held by every group slot (-1 = none); see spmm.cuh
     bool permuted = false;
     int64_t ncol_pad = 0, n_groups = 0, stream_len = 0;
@@ -78,9 +82,12 @@ struct sgl_matrix {
     int64_t nrow = 0, ncol = 0, nnz = 0;
     int64_t* colptr = nullptr;  // ncol + 1
     uint2* rec = nullptr;       // nnz records {row, value bits}
-    std::map<int, TileIndex> tiles;  // per padded rank (built lazily under tiles_mu: batch workers share the matrix)
+    std::map<int, TileIndex> tiles;  // per tile_key(padded rank, operand format) (built lazily under tiles_mu: batch workers share the matrix)
     std::mutex tiles_mu;
-    uint64_t fingerprint = 0;        // host-buffer identity for the upload cache
+    uint64_t fingerprint = 0;        // host-buffer identity for the upload cache (cheap filter)
+    uint64_t content_hash = 0;       // hash of every byte of the host p / i / x it was uploaded from
+    uint32_t vmax_bits = 0;          // bit pattern of max |value| (scale of the FP16 record values, spmm_h16.cuh)
+    bool vmax_known = false;
 };
 
 struct sgl_mask {
@@ -89,7 +96,7 @@ struct sgl_mask {
     int mask_t = 0;
     int64_t col_offset = 0, row_offset = 0;
     uint2* rec_train = nullptr;  // copy of X->rec with held-out values zeroed
-    std::map<int, uint2*> stream_train;  // its warp streams, per padded rank (lazily built)
+    std::map<int, uint2*> stream_train;  // its warp streams, per tile_key (lazily built)
     int64_t* mptr = nullptr;     // ncol + 1
     uint2* mrec = nullptr;       // held-out {row, value bits}
     int64_t mrec_cap = 0;        // records allocated (a re-seeded mask reuses the buffers)
@@ -104,6 +111,10 @@ struct sgl_handle {
     int64_t launches = 0;
     bool cache = true;
     DevBuf<float> bparts, blink, gram_f, gram_f_nojit, inv_diag;
+    // FP16 shadow of the gather operand of the SpMM in flight (spmm_h16.cuh) + {max |F| bits, 2^-se}
+    DevBuf<uint16_t> shadow;
+    DevBuf<uint32_t> shadow_meta;
+    int precision = SGL_PRECISION_MIXED16;
     DevBuf<double> part, scal, losses, gram_w;
     DevBuf<int64_t> counts;
     DevBuf<unsigned long long> workctr, held;
@@ -217,6 +228,84 @@ static void mask_release(sgl_mask* m) {
     delete m;
 }
 
+// Upload cache keys. `fingerprint_chunks` is the cheap identity of the host buffers (pointers, shape, a sample of the
+// contents): when it differs the cached device copy is certainly stale. When it matches, the candidate hit is confirmed
+// by `content_hash_chunks`, a hash of EVERY byte of p / i / x (one multi-threaded read pass, no upload), so an in-place
+// edit of a few entries or a recycled allocation with the same shape never returns the old device matrix. On a miss the
+// same hash is formed by the packing threads from the pieces they convert anyway (no extra pass).
+static inline uint64_t hash_block(const int32_t* si, const double* sx, int64_t len) {
+    const uint64_t K = 0x9E3779B97F4A7C15ull;
+    uint64_t h0 = 0x243F6A8885A308D3ull, h1 = 0x13198A2E03707344ull, h2 = 0xA4093822299F31D0ull, h3 = 0x082EFA98EC4E6C89ull;
+    int64_t t = 0;
+    for (; t + 4 <= len; t += 4) {
+        uint64_t x[4], iw[2];
+        std::memcpy(x, sx + t, 32);
+        std::memcpy(iw, si + t, 16);
+        h0 = (h0 ^ x[0]) * K; h0 ^= h0 >> 29;
+        h1 = (h1 ^ x[1]) * K; h1 ^= h1 >> 29;
+        h2 = (h2 ^ x[2] ^ iw[0]) * K; h2 ^= h2 >> 29;
+        h3 = (h3 ^ x[3] ^ (iw[1] << 1)) * K; h3 ^= h3 >> 29;
+    }
+    for (; t < len; ++t) {
+        uint64_t x;
+        std::memcpy(&x, sx + t, 8);
+        h0 = (h0 ^ x ^ ((uint64_t)(uint32_t)si[t] << 7)) * K; h0 ^= h0 >> 29;
+    }
+    return splitmix64(h0 ^ splitmix64(h1 ^ splitmix64(h2 ^ splitmix64(h3 ^ (uint64_t)len))));
+}
+static inline uint64_t hash_piece_mix(uint64_t hb, int chunk, int64_t piece) {
+    return splitmix64(hb + 0x9E3779B97F4A7C15ull * (((uint64_t)chunk << 40) ^ (uint64_t)piece ^ 0x5851F42D4C957F2Dull));
+}
+static inline uint64_t hash_pointers(const sgl_csc& c, int chunk) {  // the column pointers of one chunk
+    uint64_t h = splitmix64(0xC0FFEEull ^ (uint64_t)chunk);
+    for (int64_t t = 0; t <= c.ncol; ++t) h = (h ^ (uint64_t)(uint32_t)c.p[t]) * 0x9E3779B97F4A7C15ull, h ^= h >> 31;
+    return splitmix64(h ^ ((uint64_t)c.nrow << 1) ^ ((uint64_t)c.ncol << 33));
+}
+static constexpr int64_t HASH_PIECE = (int64_t)1 << 19;  // == sgl_handle::STAGE_RECORDS (the packing granularity)
+
+static int validate_chunk_args(const sgl_csc* c, int n) {
+    if (!c || n < 1) return fail(SGL_EINVAL, "matrix: empty chunk list");
+    for (int q = 0; q < n; ++q) {
+        if (!c[q].p) return fail(SGL_EINVAL, "matrix: NULL column pointers in chunk %d", q);
+        if (c[q].ncol < 0 || c[q].nrow < 1) return fail(SGL_EINVAL, "matrix: bad dimensions in chunk %d", q);
+        if (c[q].p[c[q].ncol] > 0 && (!c[q].i || !c[q].x)) return fail(SGL_EINVAL, "matrix: NULL slot in chunk %d", q);
+    }
+    return SGL_OK;
+}
+
+static uint64_t content_hash_chunks(const sgl_csc* c, int n) {
+    uint64_t total = 0;
+    std::vector<std::pair<int, int64_t>> pieces;
+    for (int q = 0; q < n; ++q) {
+        total ^= hash_pointers(c[q], q);
+        const int64_t nnz = c[q].p[c[q].ncol];
+        for (int64_t pc = 0; pc * HASH_PIECE < nnz; ++pc) pieces.emplace_back(q, pc);
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)(hw == 0 ? 4 : (hw > 32 ? 32 : hw));
+    if ((size_t)nt > pieces.size()) nt = (int)(pieces.size() > 0 ? pieces.size() : 1);
+    std::vector<uint64_t> acc((size_t)nt, 0);
+    auto work = [&](int wid) {
+        uint64_t a = 0;
+        for (size_t e = (size_t)wid; e < pieces.size(); e += (size_t)nt) {
+            const int q = pieces[e].first;
+            const int64_t pc = pieces[e].second, nnz = c[q].p[c[q].ncol], o = pc * HASH_PIECE;
+            const int64_t len = (nnz - o) < HASH_PIECE ? (nnz - o) : HASH_PIECE;
+            a ^= hash_piece_mix(hash_block(c[q].i + o, c[q].x + o, len), q, pc);
+        }
+        acc[(size_t)wid] = a;
+    };
+    if (nt <= 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int w = 0; w < nt; ++w) pool.emplace_back(work, w);
+        for (auto& th : pool) th.join();
+    }
+    for (uint64_t a : acc) total ^= a;
+    return total;
+}
+
 static uint64_t fingerprint_chunks(const sgl_csc* c, int n) {
     uint64_t f = 0x243F6A8885A308D3ull;
     auto mix = [&](uint64_t v) { f = splitmix64(f ^ v); };
@@ -228,7 +317,7 @@ static uint64_t fingerprint_chunks(const sgl_csc* c, int n) {
         mix((uint64_t)c[q].ncol);
         const int64_t nnz = c[q].p[c[q].ncol];
         mix((uint64_t)nnz);
-        // sample of the contents so that in-place edits of the host buffers are noticed
+        // sample of the contents: a cheap first filter (a match is confirmed by content_hash_chunks)
         const int64_t step = nnz > 4096 ? nnz / 4096 : 1;
         for (int64_t t = 0; t < nnz; t += step) {
             uint64_t bits;
@@ -293,7 +382,9 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
         return fail(SGL_ENOMEM, "matrix upload: staging cudaMalloc failed");
     }
     int rc = SGL_OK;
+    uint64_t content = 0;  // == content_hash_chunks(chunks, n_chunks), formed from the pieces as they are packed
     int64_t col_off = 0, nnz_off = 0;
+    static_assert(HASH_PIECE == (int64_t)sgl_handle::STAGE_RECORDS, "hash pieces must be the packing pieces");
     for (int q = 0; q < n_chunks && rc == SGL_OK; ++q) {
         const sgl_csc& c = chunks[q];
         const int64_t cn = c.p[c.ncol];
@@ -306,6 +397,8 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
         const int64_t n_pieces = (cn + PIECE - 1) / PIECE;
         const int nt = (int)(n_pieces < n_threads ? (n_pieces > 0 ? n_pieces : 1) : n_threads);
         std::vector<int> worker_rc((size_t)nt, 0);
+        std::vector<uint64_t> worker_hash((size_t)nt, 0);
+        content ^= hash_pointers(c, q);
         uint2* dst_dev = m->rec + nnz_off;
         const int device = h->device;
         auto worker = [&, dst_dev, device](int wid) {
@@ -319,6 +412,7 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
                 uint2* buf = h->stage[wid][use];
                 const int32_t* si = c.i + o;
                 const double* sx = c.x + o;
+                worker_hash[(size_t)wid] ^= hash_piece_mix(hash_block(si, sx, len), q, pc);
                 for (int64_t t = 0; t < len; ++t) {
                     const float v = (float)sx[t];
                     uint32_t bits;
@@ -338,8 +432,10 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
             for (int wq = 0; wq < nt; ++wq) pool.emplace_back(worker, wq);
             for (auto& th : pool) th.join();
         }
-        for (int wq = 0; wq < nt; ++wq)
+        for (int wq = 0; wq < nt; ++wq) {
+            content ^= worker_hash[(size_t)wq];
             if (worker_rc[(size_t)wq]) rc = fail(SGL_ECUDA, "matrix upload: copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
+        }
         col_off += c.ncol;
         nnz_off += cn;
     }
@@ -366,6 +462,7 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
         matrix_release(m);
         return rc;
     }
+    m->content_hash = content;
     *out = m;
     return SGL_OK;
 }
@@ -374,8 +471,13 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
 static int fill_stream(sgl_handle* h, const sgl_matrix* m, const TileIndex& ti, const uint2* rec, uint2* st) {
     const int64_t warps = ti.n_groups * ti.n_tiles;
     if (warps > 0) {
-        stream_fill_kernel<<<blocks_for(warps, 8), 256, 0, h->stream>>>(rec, m->colptr, ti.tileptr, ti.perm, ti.goff, m->ncol, ti.ncol_pad,
-                                                                     ti.n_tiles, ti.rb_rows, ti.nc, ti.pad, ti.n_groups, st);
+        if (ti.h16)
+            stream_fill_h16_kernel<<<blocks_for(warps, 8), 256, 0, h->stream>>>(
+                rec, m->colptr, ti.tileptr, ti.perm, ti.goff, ti.ncol_pad, ti.n_tiles, ti.rb_rows, ti.nc, ti.pad / 4,
+                ti.row_bytes == 64 ? 1 : 0, ti.vscale, ti.n_groups, reinterpret_cast<uint32_t*>(st));
+        else
+            stream_fill_kernel<<<blocks_for(warps, 8), 256, 0, h->stream>>>(rec, m->colptr, ti.tileptr, ti.perm, ti.goff, m->ncol, ti.ncol_pad,
+                                                                         ti.n_tiles, ti.rb_rows, ti.nc, ti.pad, ti.n_groups, st);
         LAUNCH_CHECK(h);
     }
     return SGL_OK;
@@ -383,7 +485,8 @@ static int fill_stream(sgl_handle* h, const sgl_matrix* m, const TileIndex& ti, 
 static int build_stream(sgl_handle* h, const sgl_matrix* m, const TileIndex& ti, const uint2* rec, uint2** out) {
     uint2* st = nullptr;
     // one CHUNK of slack: the kernel's last cp.async chunk of a stream may start inside the array only
-    SGL_CUDA(cudaMalloc(&st, sizeof(uint2) * (size_t)(ti.stream_len + 64)));
+    const size_t bytes = ti.h16 ? sizeof(uint32_t) * (size_t)(ti.stream_len + 128) : sizeof(uint2) * (size_t)(ti.stream_len + 64);
+    SGL_CUDA(cudaMalloc(&st, bytes));
     const int rc = fill_stream(h, m, ti, rec, st);
     if (rc != SGL_OK) {
         cudaFree(st);
@@ -423,19 +526,64 @@ static int matrix_from_dense(sgl_handle* h, const double* D, int64_t nrow, int64
     return SGL_OK;
 }
 
-// tile index for padded rank KP (lazily built, cached on the matrix)
-static int get_tiles(sgl_handle* h, sgl_matrix* m, int kpv, const TileIndex** out) {
+// the SpMM operand format for a padded rank under the handle's precision mode
+static inline bool use_h16(const sgl_handle* h, int kpv) { return h->precision == SGL_PRECISION_MIXED16 && kpv >= 32; }
+static inline int tile_key(int kpv, bool h16) { return kpv + (h16 ? 1024 : 0); }
+
+static void tile_release(TileIndex& ti) {
+    if (ti.tileptr) cudaFree(ti.tileptr);
+    if (ti.perm) cudaFree(ti.perm);
+    if (ti.goff) cudaFree(ti.goff);
+    if (ti.stream) cudaFree(ti.stream);
+    ti = TileIndex();
+}
+
+// tile index for padded rank KP and operand format (lazily built, cached on the matrix)
+static int build_tiles(sgl_handle* h, sgl_matrix* m, int kpv, bool h16, TileIndex& ti);
+static int get_tiles(sgl_handle* h, sgl_matrix* m, int kpv, bool h16, const TileIndex** out) {
     std::lock_guard<std::mutex> lock(m->tiles_mu);  // handles that share the matrix build an index once
-    auto it = m->tiles.find(kpv);
+    const int key = tile_key(kpv, h16);
+    auto it = m->tiles.find(key);
     if (it != m->tiles.end()) {
         *out = &it->second;
         return SGL_OK;
     }
-    TileIndex ti;
-    int rows = spmm_tile_rows(kpv);
+    TileIndex ti;  // built locally: a failed build leaves nothing behind in the cache
+    const int rc = build_tiles(h, m, kpv, h16, ti);
+    if (rc != SGL_OK) {
+        tile_release(ti);
+        return rc;
+    }
+    m->tiles[key] = ti;
+    *out = &m->tiles[key];
+    return SGL_OK;
+}
+static int build_tiles(sgl_handle* h, sgl_matrix* m, int kpv, bool h16, TileIndex& ti) {
+    ti.h16 = h16;
+    ti.row_bytes = h16 ? kpv * 2 : kpv * 4;
+    if (h16) {  // power-of-two scale of the FP16 record values, from max |value| of the matrix (one reduction, cached)
+        if (!m->vmax_known) {
+            SGL_TRY(h->shadow_meta.ensure(4));
+            SGL_CUDA(cudaMemsetAsync(h->shadow_meta.p + 2, 0, sizeof(uint32_t), h->stream));
+            if (m->nnz > 0) {
+                int64_t g = (m->nnz + 255) / 256;
+                if (g > 8 * h->sm_count) g = 8 * h->sm_count;
+                rec_absmax_kernel<<<(unsigned)g, 256, 0, h->stream>>>(m->rec, m->nnz, h->shadow_meta.p + 2);
+                LAUNCH_CHECK(h);
+            }
+            SGL_CUDA(cudaMemcpyAsync(&m->vmax_bits, h->shadow_meta.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+            SGL_CUDA(cudaStreamSynchronize(h->stream));
+            m->vmax_known = true;
+        }
+        const int sv = h16_scale_exp(m->vmax_bits);
+        ti.vscale = std::ldexp(1.0f, sv);
+        ti.inv_vscale = std::ldexp(1.0f, -sv);
+    }
+    int rows = h16 ? h16_tile_rows(kpv) : spmm_tile_rows(kpv);
     // small problems: shrink the tile so that (column groups x tiles) can fill the chip
     int cols_per_cta = 0;
-    DISPATCH_KP(kpv, cols_per_cta = SpmmCfg<KP>::COLS_PER_CTA);
+    if (h16) cols_per_cta = 128;
+    else DISPATCH_KP(kpv, cols_per_cta = SpmmCfg<KP>::COLS_PER_CTA);
     const int64_t groups = (m->ncol + cols_per_cta - 1) / cols_per_cta;
     if (groups < 2 * h->sm_count) {
         const int64_t want_tiles = (2 * h->sm_count + groups - 1) / (groups > 0 ? groups : 1);
@@ -453,7 +601,12 @@ static int get_tiles(sgl_handle* h, sgl_matrix* m, int kpv, const TileIndex** ou
     build_tileptr_kernel<<<grid, 256, 0, h->stream>>>(m->rec, m->colptr, m->ncol, ti.ncol_pad, ti.rb_rows, ti.n_tiles, ti.tileptr);
     LAUNCH_CHECK(h);
     // warp-stream layout: group offsets by count + exclusive scan, then one copy pass
-    DISPATCH_KP(kpv, (ti.nc = SpmmCfg<KP>::NC, ti.pad = SpmmCfg<KP>::PAD));
+    if (h16) {
+        ti.nc = 8;
+        ti.pad = 4 * (32 / (kpv / 8));  // storage is padded to blocks of four warp steps (spmm_h16.cuh)
+    } else {
+        DISPATCH_KP(kpv, (ti.nc = SpmmCfg<KP>::NC, ti.pad = SpmmCfg<KP>::PAD));
+    }
     ti.n_groups = (m->ncol + ti.nc - 1) / ti.nc;
     if (ti.n_groups < 1) ti.n_groups = 1;
     // which columns form a group: identity, unless the non-zero counts are skewed enough (genes of real data) that the
@@ -497,18 +650,19 @@ static int get_tiles(sgl_handle* h, sgl_matrix* m, int kpv, const TileIndex** ou
     const int64_t n_off = ti.n_groups * (ti.n_tiles + 1);
     SGL_TRY(h->counts.ensure((size_t)n_off + 2));
     SGL_CUDA(cudaMalloc(&ti.goff, sizeof(int64_t) * (size_t)(n_off + 1)));
-    stream_counts_kernel<<<blocks_for(n_off, 256), 256, 0, h->stream>>>(ti.tileptr, ti.perm, m->ncol, ti.ncol_pad, ti.n_tiles, ti.nc, ti.pad,
-                                                                      ti.n_groups, h->counts.p);
+    if (h16)
+        stream_counts_h16_kernel<<<blocks_for(n_off, 256), 256, 0, h->stream>>>(ti.tileptr, ti.perm, ti.ncol_pad, ti.n_tiles, ti.nc, ti.pad,
+                                                                              ti.n_groups, h->counts.p);
+    else
+        stream_counts_kernel<<<blocks_for(n_off, 256), 256, 0, h->stream>>>(ti.tileptr, ti.perm, m->ncol, ti.ncol_pad, ti.n_tiles, ti.nc,
+                                                                          ti.pad, ti.n_groups, h->counts.p);
     LAUNCH_CHECK(h);
     exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->counts.p, n_off, ti.goff);
     LAUNCH_CHECK(h);
     SGL_CUDA(cudaMemcpyAsync(&ti.stream_len, ti.goff + n_off, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     SGL_CUDA(cudaStreamSynchronize(h->stream));
-    m->tiles[kpv] = ti;
-    TileIndex& ref = m->tiles[kpv];
-    SGL_TRY(build_stream(h, m, ref, m->rec, &ref.stream));
+    SGL_TRY(build_stream(h, m, ti, m->rec, &ti.stream));
     SGL_CUDA(cudaStreamSynchronize(h->stream));  // complete before another handle's stream may read it
-    *out = &ref;
     return SGL_OK;
 }
 
@@ -558,17 +712,55 @@ static int launch_spmm(sgl_handle* h, const sgl_matrix* X, const uint2* stream, 
     return SGL_OK;
 }
 
+template <int KP>
+static int launch_spmm_h16(sgl_handle* h, const sgl_matrix* X, const uint2* stream_, const TileIndex& ti, const __half* F16,
+                           const float* inv_scale, float* Bout, int splits, int tiles_per_split) {
+    const uint32_t* stream = reinterpret_cast<const uint32_t*>(stream_);
+    using C = H16Cfg<KP>;
+    const size_t smem = 2048 + 2 * (size_t)ti.rb_rows * C::ROW_BYTES + C::RING_BYTES + 2 * sizeof(uint64_t);
+    static bool attr_done_dev[64] = {};  // function attributes are per device
+    bool& attr_done = attr_done_dev[h->device & 63];
+    if (!attr_done) {
+        SGL_CUDA(cudaFuncSetAttribute(spmm_h16_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    dim3 grid(blocks_for(ti.n_groups, C::WARPS), (unsigned)splits);
+    spmm_h16_kernel<KP><<<grid, C::WARPS * 32, smem, h->stream>>>(stream, ti.goff, ti.tileptr, ti.perm, X->ncol, ti.ncol_pad, X->nrow,
+                                                                 ti.rb_rows, ti.n_tiles, tiles_per_split, F16, inv_scale,
+                                                                 ti.inv_vscale, Bout);
+    LAUNCH_CHECK(h);
+    return SGL_OK;
+}
+
+// FP16 shadow of F (float [rows][KP]) in h->shadow, scaled by a power of two taken from max |F|; h->shadow_meta holds
+// {max bits, 2^-se as float}. Two passes over F, no host synchronisation.
+static int build_shadow(sgl_handle* h, const float* F, int64_t rows, int KPV) {
+    const int64_t n = rows * KPV;
+    SGL_TRY(h->shadow.ensure((size_t)n + 8));
+    SGL_TRY(h->shadow_meta.ensure(4));
+    SGL_CUDA(cudaMemsetAsync(h->shadow_meta.p, 0, 2 * sizeof(uint32_t), h->stream));
+    int64_t grid = (n / 4 + 255) / 256;
+    if (grid > 8 * h->sm_count) grid = 8 * h->sm_count;
+    if (grid < 1) grid = 1;
+    absmax_kernel<<<(unsigned)grid, 256, 0, h->stream>>>(F, n, h->shadow_meta.p);
+    LAUNCH_CHECK(h);
+    shadow_kernel<<<(unsigned)grid, 256, 0, h->stream>>>(F, n, h->shadow_meta.p, reinterpret_cast<__half*>(h->shadow.p),
+                                                        reinterpret_cast<float*>(h->shadow_meta.p + 1));
+    LAUNCH_CHECK(h);
+    return SGL_OK;
+}
+
 // right-hand sides b = F_in . X[:, c] for all columns of X (src/singlet.cpp:341-343) -> h->bparts as
 // [splits][ncol][KP] partial sums over row-tile ranges (summed in fixed order by the solver)
 static int dev_rhs(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask, const float* F_in, int k, int* splits_out) {
     sgl_matrix* X = const_cast<sgl_matrix*>(Xc);
     const int KPV = kp_of(k);
+    const bool h16 = use_h16(h, KPV);
     const TileIndex* ti = nullptr;
-    SGL_TRY(get_tiles(h, X, KPV, &ti));
+    SGL_TRY(get_tiles(h, X, KPV, h16, &ti));
 
-    // split the tile range when there are too few column groups to fill the chip
-    int cols_per_cta = 0;
-    DISPATCH_KP(KPV, cols_per_cta = SpmmCfg<KP>::COLS_PER_CTA);
+    int cols_per_cta = 128;
+    if (!h16) DISPATCH_KP(KPV, cols_per_cta = SpmmCfg<KP>::COLS_PER_CTA);
     const int64_t groups = (X->ncol + cols_per_cta - 1) / cols_per_cta;
     // Split the tile range when there are too few column groups to fill the chip. Cost model: the grid
     // runs in ceil(ctas / SMs) waves of ceil(n_tiles / splits) tiles each; take the cheapest split count
@@ -592,25 +784,48 @@ static int dev_rhs(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask, co
     splits = (ti->n_tiles + tiles_per_split - 1) / tiles_per_split;
     SGL_TRY(h->bparts.ensure((size_t)splits * (size_t)X->ncol * KPV));
     const uint2* rec = ti->stream;
-    if (mask) {  // training copy of the stream (held-out values zeroed), built once per padded rank
+    if (mask) {  // training copy of the stream (held-out values zeroed), built once per padded rank and format
         sgl_mask* mm = const_cast<sgl_mask*>(mask);
-        auto it = mm->stream_train.find(KPV);
+        const int key = tile_key(KPV, h16);
+        auto it = mm->stream_train.find(key);
         if (it == mm->stream_train.end()) {
             uint2* st = nullptr;
             SGL_TRY(build_stream(h, X, *ti, mask->rec_train, &st));
-            mm->stream_train[KPV] = st;
+            mm->stream_train[key] = st;
             rec = st;
         } else {
             rec = it->second;
         }
     }
+    if (h16) SGL_TRY(build_shadow(h, F_in, X->nrow, KPV));
     {
         // algorithmic bytes of this launch: 8*nnz + 4*(ncol+1) + 4*k*nrow + 4*k*ncol
         ProfScope ps(h, PK_SPMM, 8 * X->nnz + 4 * (X->ncol + 1) + 4ll * k * X->nrow + 4ll * k * X->ncol);
-        DISPATCH_KP(KPV, SGL_TRY(launch_spmm<KP>(h, X, rec, *ti, F_in, h->bparts.p, splits, tiles_per_split)));
+        if (h16) {
+            const __half* f16 = reinterpret_cast<const __half*>(h->shadow.p);
+            const float* inv = reinterpret_cast<const float*>(h->shadow_meta.p + 1);
+            switch (KPV) {
+                case 32: SGL_TRY(launch_spmm_h16<32>(h, X, rec, *ti, f16, inv, h->bparts.p, splits, tiles_per_split)); break;
+                case 64: SGL_TRY(launch_spmm_h16<64>(h, X, rec, *ti, f16, inv, h->bparts.p, splits, tiles_per_split)); break;
+                case 128: SGL_TRY(launch_spmm_h16<128>(h, X, rec, *ti, f16, inv, h->bparts.p, splits, tiles_per_split)); break;
+                default: return fail(SGL_EINVAL, "16-bit operand SpMM: unsupported padded rank %d", KPV);
+            }
+        } else {
+            DISPATCH_KP(KPV, SGL_TRY(launch_spmm<KP>(h, X, rec, *ti, F_in, h->bparts.p, splits, tiles_per_split)));
+        }
     }
     *splits_out = splits;
     return SGL_OK;
+}
+
+struct ConstGramGuard {  // serialises the users of the __constant__ Gram (nnls.cuh) of one device
+    std::mutex mu;
+    cudaEvent_t ev = nullptr;
+    cudaStream_t last_stream = nullptr;
+};
+static ConstGramGuard& const_gram_guard(int device) {
+    static ConstGramGuard guards[64];
+    return guards[device & 63];
 }
 
 // coordinate-descent solves for `ncol` columns (src/singlet.cpp:229-250 via :345 / :464). Bparts is
@@ -652,7 +867,12 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
                 if (st[3]) fprintf(stderr, "[nnls] previous launch: %llu columns, mean sweeps %.2f\n", st[3], (double)st[2] / (double)st[3]);
             }
             SGL_CUDA(cudaMemsetAsync(h->workctr.p, 0, 4 * sizeof(unsigned long long), h->stream));
-            // Gram + reciprocal diagonal -> constant memory (uniform-datapath operands of the solver)
+            // Gram + reciprocal diagonal -> constant memory (uniform-datapath operands of the solver). The symbols are
+            // per device, not per handle: handles on other streams of this device are held back (stream-ordered, no host
+            // wait) until the solver that reads the current contents has finished, and the host section is under a mutex.
+            ConstGramGuard& cg = const_gram_guard(h->device);
+            std::lock_guard<std::mutex> cg_lock(cg.mu);
+            if (cg.ev && cg.last_stream != h->stream) SGL_CUDA(cudaStreamWaitEvent(h->stream, cg.ev, 0));
             SGL_CUDA(cudaMemcpyToSymbolAsync(c_gram, h->gram_f.p, sizeof(float) * KPV * KPV, 0, cudaMemcpyDeviceToDevice, h->stream));
             SGL_CUDA(cudaMemcpyToSymbolAsync(c_inv_diag, h->inv_diag.p, sizeof(float) * KPV, 0, cudaMemcpyDeviceToDevice, h->stream));
             switch (KPV) {
@@ -677,6 +897,9 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
 #undef NNLS_CASE
             }
             LAUNCH_CHECK(h);
+            if (!cg.ev) SGL_CUDA(cudaEventCreateWithFlags(&cg.ev, cudaEventDisableTiming));
+            SGL_CUDA(cudaEventRecord(cg.ev, h->stream));
+            cg.last_stream = h->stream;
             // row sums of the new solution (the local part of scale's d)
             n_parts = (ncol + 255) / 256;
             if (n_parts > 2 * h->sm_count) n_parts = 2 * h->sm_count;
@@ -963,8 +1186,9 @@ static void drop_masks(sgl_handle* h, sgl_mask** mask_slot) {
 }
 static int cached_upload(sgl_handle* h, const sgl_csc* chunks, int n, sgl_matrix** slot, sgl_mask** mask_slot,
                          sgl_matrix** out) {
+    SGL_TRY(validate_chunk_args(chunks, n));
     const uint64_t fp = fingerprint_chunks(chunks, n);
-    if (h->cache && *slot && (*slot)->fingerprint == fp) {
+    if (h->cache && *slot && (*slot)->fingerprint == fp && (*slot)->content_hash == content_hash_chunks(chunks, n)) {
         *out = *slot;
         return SGL_OK;
     }
@@ -1203,6 +1427,7 @@ int sgl_create(int device, void* stream, sgl_handle** out) {
         delete h;
         return fail(SGL_ENOMEM, "cudaMallocHost failed");
     }
+    if (const char* ev = getenv("SGL_PRECISION")) h->precision = (ev[0] == 'f' || ev[0] == 'F') ? SGL_PRECISION_FP32 : SGL_PRECISION_MIXED16;
     *out = h;
     return SGL_OK;
 }
@@ -1220,6 +1445,7 @@ int sgl_destroy(sgl_handle* h) {
     h->bparts.release(); h->blink.release(); h->gram_f.release(); h->gram_f_nojit.release(); h->inv_diag.release();
     h->part.release(); h->scal.release(); h->losses.release(); h->gram_w.release(); h->counts.release(); h->workctr.release(); h->held.release();
     h->fitW.release(); h->fitH.release(); h->fitWprev.release(); h->fit_small.release(); h->ftmp.release();
+    h->shadow.release(); h->shadow_meta.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -1234,6 +1460,14 @@ int sgl_destroy(sgl_handle* h) {
     delete h;
     return SGL_OK;
 }
+int sgl_set_precision(sgl_handle* h, int mode) {
+    if (!h) return fail(SGL_EINVAL, "NULL handle");
+    if (mode != SGL_PRECISION_MIXED16 && mode != SGL_PRECISION_FP32) return fail(SGL_EINVAL, "unknown precision mode %d", mode);
+    h->precision = mode;
+    for (sgl_handle* c : h->children) c->precision = mode;
+    return SGL_OK;
+}
+int sgl_get_precision(sgl_handle* h) { return h ? h->precision : SGL_EINVAL; }
 int sgl_set_cache(sgl_handle* h, int enabled) {
     if (!h) return fail(SGL_EINVAL, "NULL handle");
     h->cache = enabled != 0;
@@ -1290,18 +1524,42 @@ int sgl_nmf(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, int nA
     return nmf_on_device(h, A, At, tol, maxit, L1_w, L1_h, L2_w, L2_h, k, w, d, h_out, iters_out, tol_out, cb);
 }
 
-// dense uploads share the handle's cache slots (keyed by pointer, shape and a content sample)
+// dense uploads share the handle's cache slots (keyed by pointer, shape and a hash of every byte)
 static int cached_dense(sgl_handle* h, const double* D, int64_t nrow, int64_t ncol, sgl_matrix** slot, sgl_mask** mask_slot,
                         sgl_matrix** out) {
     if (!D) return fail(SGL_EINVAL, "dense matrix is NULL");
+    if (nrow < 1 || ncol < 0) return fail(SGL_EINVAL, "dense matrix: bad dimensions");
     uint64_t fp = splitmix64(0xD3115Eull ^ (uint64_t)(uintptr_t)D);
     fp = splitmix64(fp ^ (uint64_t)nrow);
     fp = splitmix64(fp ^ ((uint64_t)ncol << 1));
-    const int64_t tot = nrow * ncol, step = tot > 4096 ? tot / 4096 : 1;
-    for (int64_t t = 0; t < tot; t += step) {
-        uint64_t bits;
-        std::memcpy(&bits, &D[t], 8);
-        fp = splitmix64(fp ^ bits);
+    {  // every byte of the dense input (these matrices are small next to the sparse ones): threads over 4 MB pieces
+        const int64_t tot = nrow * ncol, PIECE = (int64_t)1 << 19, n_pieces = (tot + PIECE - 1) / PIECE;
+        unsigned hw = std::thread::hardware_concurrency();
+        int nt = (int)(hw == 0 ? 4 : (hw > 32 ? 32 : hw));
+        if ((int64_t)nt > n_pieces) nt = (int)(n_pieces > 0 ? n_pieces : 1);
+        std::vector<uint64_t> acc((size_t)nt, 0);
+        auto work = [&](int wid) {
+            const uint64_t K = 0x9E3779B97F4A7C15ull;
+            for (int64_t pc = wid; pc < n_pieces; pc += nt) {
+                const int64_t o = pc * PIECE, len = (tot - o) < PIECE ? (tot - o) : PIECE;
+                uint64_t hh = splitmix64((uint64_t)pc);
+                for (int64_t t = 0; t < len; ++t) {
+                    uint64_t bits;
+                    std::memcpy(&bits, &D[o + t], 8);
+                    hh = (hh ^ bits) * K;
+                    hh ^= hh >> 29;
+                }
+                acc[(size_t)wid] ^= splitmix64(hh);
+            }
+        };
+        if (nt <= 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int w = 0; w < nt; ++w) pool.emplace_back(work, w);
+            for (auto& th : pool) th.join();
+        }
+        for (uint64_t a : acc) fp ^= a;
     }
     if (h->cache && *slot && (*slot)->fingerprint == fp) {
         *out = *slot;
@@ -1434,6 +1692,12 @@ static int ard_on_device(sgl_handle* h, sgl_matrix* A, sgl_matrix* At, double to
                          double* d, double* h_out, uint64_t seed, uint64_t inv_density, double overfit_threshold,
                          uint16_t trace_test_mse, sgl_trace* tr, const sgl_callbacks* cb) {
     SGL_TRY(check_shapes(A, At));
+    {  // the trace holds one entry per traced iteration plus the trailing one (src/singlet.cpp:1116-1141)
+        const int need = (int)maxit / (int)trace_test_mse + 2;
+        if (!tr->test_mse || !tr->iter || !tr->tol || !tr->score_overfit || tr->capacity < need)
+            return fail(SGL_EINVAL, "trace capacity %d too small: maxit %d with trace_test_mse %d needs %d entries", (int)tr->capacity,
+                        (int)maxit, (int)trace_test_mse, need);
+    }
     sgl_mask *mA = nullptr, *mAt = nullptr;
     SGL_TRY(cached_mask(h, A, seed, inv_density, 0, &h->cmA, &mA));
     SGL_TRY(cached_mask(h, At, seed, inv_density, 1, &h->cmAt, &mAt));
@@ -1509,8 +1773,8 @@ int sgl_ard_nmf_batch(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* A
         if (!used) continue;
         ++n_kp;
         const TileIndex* ti = nullptr;
-        SGL_TRY(get_tiles(h, A, kp, &ti));
-        SGL_TRY(get_tiles(h, At, kp, &ti));
+        SGL_TRY(get_tiles(h, A, kp, use_h16(h, kp), &ti));
+        SGL_TRY(get_tiles(h, At, kp, use_h16(h, kp), &ti));
     }
     // workers: bounded by the jobs, by 8, and by what the masks + training streams of a worker may take of the free memory
     int conc = concurrency > 0 ? concurrency : 4;
@@ -1530,6 +1794,7 @@ int sgl_ard_nmf_batch(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* A
         SGL_TRY(sgl_create(h->device, nullptr, &c));
         h->children.push_back(c);
     }
+    for (sgl_handle* c : h->children) c->precision = h->precision;
     // largest ranks first (they take longest), ties in caller order
     std::vector<int> order((size_t)n_jobs);
     for (int j = 0; j < n_jobs; ++j) order[(size_t)j] = j;
