@@ -182,6 +182,21 @@ struct ProfScope {  // records an event pair around the launches issued in its l
 
 static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
+// SGL_TIMING=1: wall-clock phases of the host-facing entry points on stderr (developer aid; synchronises the stream)
+struct PhaseTimer {
+    sgl_handle* h;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTimer(sgl_handle* h_) : h(h_), on(getenv("SGL_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(h->stream);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sgl timing] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 #define DISPATCH_KP(KPV, ...)                          \
     switch (KPV) {                                     \
         case 4: { constexpr int KP = 4; __VA_ARGS__; } break;     \
@@ -1519,9 +1534,14 @@ int sgl_nmf(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* At_, int nA
     SGL_TRY(check_k(k));
     SGL_TRY(set_device(h));
     sgl_matrix *A = nullptr, *At = nullptr;
+    PhaseTimer pt(h);
     SGL_TRY(cached_upload(h, A_, nA, &h->cA, &h->cmA, &A));
+    pt.mark("upload A");
     SGL_TRY(cached_At(h, At_, nAt, A, &At));
-    return nmf_on_device(h, A, At, tol, maxit, L1_w, L1_h, L2_w, L2_h, k, w, d, h_out, iters_out, tol_out, cb);
+    pt.mark(At_ ? "upload At" : "transpose on device");
+    const int rc = nmf_on_device(h, A, At, tol, maxit, L1_w, L1_h, L2_w, L2_h, k, w, d, h_out, iters_out, tol_out, cb);
+    pt.mark("fit (init, iterations, download)");
+    return rc;
 }
 
 // dense uploads share the handle's cache slots (keyed by pointer, shape and a hash of every byte)
@@ -1609,17 +1629,23 @@ static int nmf_on_device(sgl_handle* h, sgl_matrix* A, sgl_matrix* At, double to
                          const sgl_callbacks* cb) {
     SGL_TRY(check_shapes(A, At));
     FitBuffers fb;
+    PhaseTimer pt(h);
     SGL_TRY(fit_init(h, fb, k, A->nrow, A->ncol, w));
+    pt.mark("  fit_init");
     double tol_ = 1;
     uint16_t iter_ = 0;
     for (; iter_ < maxit && tol_ > tol; ++iter_) {  // src/singlet.cpp:647
         SGL_TRY(als_iteration(h, fb, A, At, nullptr, nullptr, k, L1_w, L1_h, L2_w, L2_h, cb, &tol_));
+        if (iter_ == 0) pt.mark("  first iteration (+ tiles)");
         if (cb && cb->on_iter) cb->on_iter(cb->user, iter_ + 1, tol_, NAN);
         if (cb && cb->poll_interrupt && cb->poll_interrupt(cb->user)) return fail(SGL_EINTERRUPT, "interrupted");
     }
+    pt.mark("  other iterations");
     if (iters_out) *iters_out = iter_;
     if (tol_out) *tol_out = tol_;
-    return fit_outputs(h, fb, k, A->nrow, A->ncol, w, d, h_out);
+    const int rc = fit_outputs(h, fb, k, A->nrow, A->ncol, w, d, h_out);
+    pt.mark("  download");
+    return rc;
 }
 
 // ---- c_linked_nmf ("next" row f2) ---------------------------------------------------------
