@@ -468,6 +468,35 @@ def test_pbmc3k_against_reference_goldens(handle, oracle):
     assert list(cv["iter"]) == list(z["cv_iter"]) and np.allclose(cv["test_mse"], z["cv_test_mse"], rtol=MSE_RTOL)
 
 
+def test_whole_cv_sweep_against_reference_goldens(handle):
+    """ALL 87 fits of BASELINE configs[1] -- set.seed(123); cross_validate_nmf(A, ranks = 2:30, n_replicates = 3) on pbmc3k --
+    through the batched GPU sweep (sgl_ard_nmf_batch), against the per-fit traces produced by the reference's own compiled
+    code (tests/golden/ref_pbmc3k_cv.npz, scripts/make_cv_goldens.py). Every fit must trace the same iterations (same
+    convergence / overfit decisions) with every test error within 1e-4 relative."""
+    import os
+
+    from singlet_b200 import api
+    from singlet_b200.datasets import get_pbmc3k_data, log_normalize
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pbmc3k_cv.npz"))
+    A = log_normalize(get_pbmc3k_data())
+    api.set_seed(123)
+    df = api.cross_validate_nmf(A, list(range(2, 31)), n_replicates=3, verbose=0, handle=handle)
+    assert len(z["k"]) == 87
+    worst, mismatched = 0.0, []
+    for q in range(87):
+        k, rep, nt = int(z["k"][q]), int(z["rep"][q]), int(z["n_trace"][q])
+        rows = df[(df["k"] == k) & (df["rep"] == rep)]
+        it_dev, it_ref = list(rows["iter"]), list(z["iter"][q, :nt])
+        if it_dev != it_ref:
+            mismatched.append((k, rep, it_dev, it_ref))
+            continue
+        rel = np.abs(rows["test_error"].to_numpy() - z["test_mse"][q, :nt]) / z["test_mse"][q, :nt]
+        worst = max(worst, float(rel.max()))
+    assert not mismatched, mismatched
+    assert worst <= MSE_RTOL, worst
+
+
 def test_device_train_and_test_mse(oracle):
     """The fused MSE kernel: held-out (test, src/singlet.cpp:536-568) and not-held-out (train, harness-defined) means."""
     from singlet_b200 import synth
