@@ -388,6 +388,132 @@ def main():
     return 0
 
 
+def extras_legs(device):
+    """BASELINE configs[0], [1] and [3] through the public API on one GPU (seconds, wall clock, host matrices in, models
+    out), with the reference CPU code timed live on the same fits where that takes seconds (C1, four fits of the C2 sweep)."""
+    import scipy.sparse as sp
+
+    from oracle.pyoracle import Oracle, have_reference
+    from singlet_b200 import api, synth
+    from singlet_b200.datasets import get_pbmc3k_data, log_normalize
+    from singlet_b200.rrng import RRng
+    from singlet_b200.sharded import CudaBackend
+
+    res = {}
+    orc = Oracle("reference" if have_reference() else "port")
+    cores = max(orc.max_threads(), os.cpu_count() or 1)
+    A = log_normalize(get_pbmc3k_data())
+    At = A.T.tocsc()
+    At.sort_indices()
+    h = api.Handle(device)
+    # ---- configs[0]: set.seed(123); run_nmf(A, rank = 10) on pbmc3k ----
+    api.set_seed(123)
+    api.run_nmf(A, 10, maxit=2, verbose=False, handle=h)  # warm-up (module load, allocator, padded rank 16)
+    h.set_cache(False)
+    api.set_seed(123)
+    t0 = time.perf_counter()
+    model = api.run_nmf(A, 10, verbose=False, handle=h)
+    c1_gpu = time.perf_counter() - t0
+    h.set_cache(True)
+    w10 = RRng(123).matrix_runif(10, A.shape[0])
+    t0 = time.perf_counter()
+    orc.nmf(A, At, w10, tol=1e-4, maxit=100, L1=(0.01, 0.01), threads=cores)
+    c1_cpu = time.perf_counter() - t0
+    res["c1_run_nmf"] = {"workload": "pbmc3k 13,714 x 2,700 log-normalised, set.seed(123); run_nmf(A, rank = 10), tol 1e-4",
+                         "seconds": c1_gpu, "iterations": int(model["iter"]), "cpu_reference_seconds": c1_cpu, "cpu_cores": cores,
+                         "cpu_kind": orc.kind}
+    # ---- configs[1]: set.seed(123); cross_validate_nmf(A, ranks = 2:30, n_replicates = 3) ----
+    ranks = list(range(2, 31))
+    api.set_seed(123)
+    t0 = time.perf_counter()
+    df = api.cross_validate_nmf(A, ranks, n_replicates=3, verbose=0, handle=h)
+    cv_first = time.perf_counter() - t0
+    api.set_seed(123)
+    t0 = time.perf_counter()
+    api.cross_validate_nmf(A, ranks, n_replicates=3, verbose=0, handle=h)
+    cv_again = time.perf_counter() - t0
+    # reference CPU on four fits of replicate 1 (the whole sweep takes minutes): seconds per fit interpolated over k
+    r = RRng(123)
+    w_init = [r.matrix_runif(max(ranks), A.shape[0]) for _ in range(3)]
+    seed1 = abs(r.dot_random_seed(3 + 1))
+    sampled = {}
+    for kk in (2, 11, 20, 30):
+        t0 = time.perf_counter()
+        orc.ard_nmf(A, At, w_init[0][:kk, :], seed1, 20, tol=1e-4, maxit=100, L1=0.01, L2=0.0, threads=cores, overfit_threshold=1e-4,
+                    trace_test_mse=5)
+        sampled[kk] = time.perf_counter() - t0
+    ks = sorted(sampled)
+    est = 3.0 * float(sum(np.interp(kq, ks, [sampled[q] for q in ks]) for kq in ranks))
+    golden = None
+    try:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "ref_pbmc3k_cv.npz"))
+        golden = {"seconds": float(z["total_seconds"]), "threads": int(z["threads"]),
+                  "note": "the whole sweep by the reference-compiled code in the build container (scripts/make_cv_goldens.py)"}
+    except Exception:
+        pass
+    last = df.loc[df.groupby(["rep", "k"])["iter"].idxmax()]
+    res["cv_sweep"] = {"workload": "pbmc3k, set.seed(123); cross_validate_nmf(A, ranks = 2:30, n_replicates = 3, test_density = 0.05): 87 fits",
+                       "seconds": cv_first, "seconds_repeated_call": cv_again, "fits": len(ranks) * 3,
+                       "best_rank": int(api.GetBestRank(df)),
+                       "test_error_k10_rep1": float(last[(last["k"] == 10) & (last["rep"] == 1)]["test_error"].iloc[0]),
+                       "cpu_reference": {"seconds_estimated": est, "cores": cores, "kind": orc.kind,
+                                         "sampled_fit_seconds_rep1": {str(q): sampled[q] for q in ks},
+                                         "how": "four fits of replicate 1 timed live; seconds per fit interpolated linearly over k, x 3 replicates",
+                                         "build_container_full_sweep": golden}}
+    h.close()
+    # ---- configs[3]: ard_nmf on synthetic 20k x 250k, 8 % (structure-free: the search stops at its first bracket) and on a
+    # matrix of the same gene count with a planted rank (the search walks) ----
+    m4, n4, d4 = 20000, 250000, 0.08
+    be = CudaBackend(device)
+    hm = be.synth(m4, n4, d4, synth.DATA_SEED, 0, 0, n4, synth.values_table(m4, d4))
+    p4 = be.matrix_to_host(hm)  # the host matrix a user hands to ard_nmf
+    be.close()
+    A4 = sp.csc_matrix((p4[2], p4[1], p4[0]), shape=(m4, n4))
+    A4.has_sorted_indices = True
+    h = api.Handle(device)
+    api.set_seed(123)
+    t0 = time.perf_counter()
+    mod = api.ard_nmf(A4, L1=0.01, verbose=0, handle=h)
+    c4 = time.perf_counter() - t0
+    cv = mod["cv_data"]
+    res["c4_ard_nmf"] = {"workload": "synthetic 20k x 250k, 8 % density, ard_nmf(A, L1 = 0.01) defaults", "seconds": c4, "nnz": int(A4.nnz),
+                         "ranks_tried": [int(q) for q in sorted(cv["k"].unique())], "best_rank": int(mod["w"].shape[1]),
+                         "final_iterations": int(mod["iter"])}
+    del A4, mod
+    Ap = planted_counts(m4, 25000, 12, d4, seed=7)
+    api.set_seed(123)
+    t0 = time.perf_counter()
+    mod = api.ard_nmf(Ap, L1=0.01, k_max=64, verbose=0, handle=h)
+    cp = time.perf_counter() - t0
+    cv = mod["cv_data"]
+    res["c4_ard_nmf"]["planted_rank_12"] = {"workload": "20k x 25k Poisson counts of a rank-12 non-negative model, log-normalised, ~8 % density",
+                                            "seconds": cp, "nnz": int(Ap.nnz), "ranks_tried": [int(q) for q in cv["k"].unique()],
+                                            "best_rank": int(mod["w"].shape[1]), "final_iterations": int(mod["iter"])}
+    h.close()
+    return res
+
+
+def planted_counts(m, n, rank, density, seed):
+    """Sparse log-normalised counts with a planted non-negative rank (column blocks keep the dense intermediate small)."""
+    import scipy.sparse as sp
+
+    rs = np.random.RandomState(seed)
+    W0 = rs.gamma(0.3, 1.0, size=(m, rank)) * (rs.rand(m, rank) < 0.3)
+    blocks = []
+    for c0 in range(0, n, 2500):
+        nb = min(2500, n - c0)
+        H0 = rs.gamma(0.5, 1.0, size=(rank, nb)) * (rs.rand(rank, nb) < 0.4)
+        lam = W0 @ H0
+        lam *= (-np.log1p(-density)) / max(lam.mean(), 1e-300)
+        blocks.append(sp.csc_matrix(rs.poisson(lam).astype(np.float64)))
+    X = sp.hstack(blocks, format="csc")
+    colsum = np.asarray(X.sum(axis=0)).ravel()
+    colsum[colsum == 0] = 1.0
+    X.data = np.log1p(X.data / np.repeat(colsum, np.diff(X.indptr)) * 1e4)
+    X.sort_indices()
+    return X
+
+
 def e2e_leg_sharded(be, cfg, steps, A_dev, At_dev, rank, world, group):
     """N > 1: every rank starts from HOST dgCMatrix shards (its cells, and the transpose of that block), uploads
     them, runs `steps` iterations of the sharded fit and downloads the replicated model. Max over ranks."""

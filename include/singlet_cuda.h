@@ -77,13 +77,18 @@ int sgl_destroy(sgl_handle* h);
 int sgl_set_cache(sgl_handle* h, int enabled);
 /* Operand precision of the sparse product b = sum v * F[r, :] (src/singlet.cpp:341-343). Accumulation is FP32 in both
  * modes, the non-zero values v stay FP32, the solver, Gram, scale, cor and loss kernels are unaffected.
- *   SGL_PRECISION_MIXED16 (default): for padded ranks >= 32 the gathered factor F is staged as FP16 scaled by a power
- *       of two taken from max |F| (relative rounding 2^-12 per element, averaged over the non-zeros of a column);
- *       this halves the shared-memory gather that bounds the kernel.
- *   SGL_PRECISION_FP32: F is gathered in FP32 (the round-1 kernel).
- * The environment variable SGL_PRECISION=fp32 selects the FP32 mode for handles created afterwards. */
+ *   SGL_PRECISION_MIXED16 (default): for padded ranks >= 32, on matrices with >= 256 non-zeros per row AND per column on
+ *       average, the gathered factor F is staged as FP16 scaled by a power of two taken from max |F| and the non-zero
+ *       values as stochastically rounded FP16 scaled by a power of two taken from max |v| (zero-mean relative rounding
+ *       of 2^-12 / 2^-11 per element, averaged over the non-zeros of a column: ~1e-5 of a right-hand side at the BASELINE
+ *       configs); every product is exact in FP32 and accumulated in FP32. This halves the shared-memory gather that bounds
+ *       the kernel. Smaller matrices and ranks keep FP32 operands.
+ *   SGL_PRECISION_FP32: F and v are gathered in FP32 (the round-1 kernel) whatever the matrix.
+ *   SGL_PRECISION_MIXED16_ALWAYS: 16-bit staging for every matrix at padded ranks >= 32 (tests).
+ * The environment variable SGL_PRECISION=fp32 | always | mixed16 sets the mode of handles created afterwards. */
 #define SGL_PRECISION_MIXED16 0
 #define SGL_PRECISION_FP32 1
+#define SGL_PRECISION_MIXED16_ALWAYS 2
 int sgl_set_precision(sgl_handle* h, int mode);
 int sgl_get_precision(sgl_handle* h);
 int sgl_synchronize(sgl_handle* h);

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsinglet_cuda.so")
 
 SGL_OK, SGL_EINVAL, SGL_ENODEVICE, SGL_ECUDA, SGL_EINTERRUPT, SGL_ENOMEM = 0, -1, -2, -3, -4, -5
 MAX_RANK = 128
-PRECISION_MIXED16, PRECISION_FP32 = 0, 1
+PRECISION_MIXED16, PRECISION_FP32, PRECISION_MIXED16_ALWAYS = 0, 1, 2
 
 
 class SingletCudaError(RuntimeError):

@@ -61,8 +61,9 @@ class Handle:
         return int(self.lib.sgl_launch_count(self._h))
 
     def set_precision(self, mode):
-        """``"mixed16"`` (default: FP16-staged gather operand, FP32 accumulation) or ``"fp32"`` (sgl_set_precision)."""
-        code = {"mixed16": _lib.PRECISION_MIXED16, "fp32": _lib.PRECISION_FP32}.get(mode, mode)
+        """``"mixed16"`` (default: FP16-staged operands of the sparse product on large matrices at padded rank >= 32, FP32
+        accumulation), ``"fp32"``, or ``"mixed16_always"`` (16-bit staging whatever the matrix size) -- sgl_set_precision."""
+        code = {"mixed16": _lib.PRECISION_MIXED16, "fp32": _lib.PRECISION_FP32, "mixed16_always": _lib.PRECISION_MIXED16_ALWAYS}.get(mode, mode)
         _lib.check(self.lib.sgl_set_precision(self._h, int(code)))
 
     def set_cache(self, enabled: bool):
@@ -399,8 +400,10 @@ def _sort_model(model, rank):
     """R/run_nmf.R:65-71: order by d decreasing; w <- t(w)[, idx] (m x k); h <- h[idx, ]."""
     idx = np.argsort(-model["d"], kind="stable")
     model["d"] = model["d"][idx]
-    model["w"] = np.ascontiguousarray(model["w"].T[:, idx])
-    model["h"] = np.ascontiguousarray(model["h"][idx, :])
+    # the engine's factors are column-major k x cols, i.e. C-ordered (cols, k) arrays seen through .T: permuting the LAST
+    # axis of those views is one streaming pass (h is k x n = 256 MB at the headline config), no layout conversion
+    model["w"] = np.take(np.asarray(model["w"]).T, idx, axis=1)        # m x k
+    model["h"] = np.take(np.asarray(model["h"]).T, idx, axis=1).T      # k x n (column-major)
     model["names"] = ["NMF_%d" % (i + 1) for i in range(model["w"].shape[1])]
     return model
 

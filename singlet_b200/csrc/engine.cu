@@ -542,7 +542,15 @@ static int matrix_from_dense(sgl_handle* h, const double* D, int64_t nrow, int64
 }
 
 // the SpMM operand format for a padded rank under the handle's precision mode
-static inline bool use_h16(const sgl_handle* h, int kpv) { return h->precision == SGL_PRECISION_MIXED16 && kpv >= 32; }
+// 16-bit staging needs padded rank >= 32 (below that the gather is not the bound) and, in the default mode, a matrix whose
+// rows and columns hold >= 256 non-zeros on average: the zero-mean operand rounding (2^-12 per element) then averages to
+// <= ~2e-5 of a right-hand side. Small matrices (pbmc3k: 166 non-zeros per gene) gain nothing from it and keep FP32 operands.
+static inline bool use_h16(const sgl_handle* h, int kpv, const sgl_matrix* X) {
+    if (kpv < 32 || h->precision == SGL_PRECISION_FP32) return false;
+    if (h->precision == SGL_PRECISION_MIXED16_ALWAYS) return true;
+    const int64_t longer = X->nrow > X->ncol ? X->nrow : X->ncol;
+    return X->nnz >= 256 * longer;
+}
 static inline int tile_key(int kpv, bool h16) { return kpv + (h16 ? 1024 : 0); }
 
 static void tile_release(TileIndex& ti) {
@@ -770,7 +778,7 @@ static int build_shadow(sgl_handle* h, const float* F, int64_t rows, int KPV) {
 static int dev_rhs(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask, const float* F_in, int k, int* splits_out) {
     sgl_matrix* X = const_cast<sgl_matrix*>(Xc);
     const int KPV = kp_of(k);
-    const bool h16 = use_h16(h, KPV);
+    const bool h16 = use_h16(h, KPV, X);
     const TileIndex* ti = nullptr;
     SGL_TRY(get_tiles(h, X, KPV, h16, &ti));
 
@@ -1442,7 +1450,8 @@ int sgl_create(int device, void* stream, sgl_handle** out) {
         delete h;
         return fail(SGL_ENOMEM, "cudaMallocHost failed");
     }
-    if (const char* ev = getenv("SGL_PRECISION")) h->precision = (ev[0] == 'f' || ev[0] == 'F') ? SGL_PRECISION_FP32 : SGL_PRECISION_MIXED16;
+    if (const char* ev = getenv("SGL_PRECISION"))
+        h->precision = (ev[0] == 'f' || ev[0] == 'F') ? SGL_PRECISION_FP32 : ((ev[0] == 'a' || ev[0] == 'A') ? SGL_PRECISION_MIXED16_ALWAYS : SGL_PRECISION_MIXED16);
     *out = h;
     return SGL_OK;
 }
@@ -1477,7 +1486,8 @@ int sgl_destroy(sgl_handle* h) {
 }
 int sgl_set_precision(sgl_handle* h, int mode) {
     if (!h) return fail(SGL_EINVAL, "NULL handle");
-    if (mode != SGL_PRECISION_MIXED16 && mode != SGL_PRECISION_FP32) return fail(SGL_EINVAL, "unknown precision mode %d", mode);
+    if (mode != SGL_PRECISION_MIXED16 && mode != SGL_PRECISION_FP32 && mode != SGL_PRECISION_MIXED16_ALWAYS)
+        return fail(SGL_EINVAL, "unknown precision mode %d", mode);
     h->precision = mode;
     for (sgl_handle* c : h->children) c->precision = mode;
     return SGL_OK;
@@ -1799,8 +1809,8 @@ int sgl_ard_nmf_batch(sgl_handle* h, const sgl_csc* A_, int nA, const sgl_csc* A
         if (!used) continue;
         ++n_kp;
         const TileIndex* ti = nullptr;
-        SGL_TRY(get_tiles(h, A, kp, use_h16(h, kp), &ti));
-        SGL_TRY(get_tiles(h, At, kp, use_h16(h, kp), &ti));
+        SGL_TRY(get_tiles(h, A, kp, use_h16(h, kp, A), &ti));
+        SGL_TRY(get_tiles(h, At, kp, use_h16(h, kp, At), &ti));
     }
     // workers: bounded by the jobs, by 8, and by what the masks + training streams of a worker may take of the free memory
     int conc = concurrency > 0 ? concurrency : 4;

@@ -129,32 +129,42 @@ def test_predict_mixed16_matches_oracle(handle, oracle, k):
     m, n = 700, 450
     A, At = _mk(m, n, 0.08, seed=k, empty_cols=(0, 17, n - 1))
     w = synth.w_init(k, m, seed=k + 1)
-    for L1, L2 in ((0.0, 0.0), (0.01, 0.0)):
-        dev = api.Rcpp_predict(A, w, L1, L2, 0)
-        ref = oracle.predict(A, w, np.zeros((k, n)), L1, L2)
-        assert np.all(dev[:, [0, 17, n - 1]] == 0)
-        scale = np.abs(ref).max()
-        assert np.abs(dev - ref).max() <= 2e-3 * scale, (k, L1, L2, np.abs(dev - ref).max() / scale)
-        cols = [c for c in range(n) if ref[:, c].std() > 0]
-        cors = [np.corrcoef(dev[:, c], ref[:, c])[0, 1] for c in cols]
-        assert min(cors) >= 0.9999, (k, min(cors))
+    handle.set_precision("mixed16_always")  # this matrix is far below the size at which the default mode stages in 16 bits
+    try:
+        for L1, L2 in ((0.0, 0.0), (0.01, 0.0)):
+            dev = api.Rcpp_predict(A, w, L1, L2, 0)
+            ref = oracle.predict(A, w, np.zeros((k, n)), L1, L2)
+            assert np.all(dev[:, [0, 17, n - 1]] == 0)
+            scale = np.abs(ref).max()
+            assert np.abs(dev - ref).max() <= 2e-3 * scale, (k, L1, L2, np.abs(dev - ref).max() / scale)
+            cols = [c for c in range(n) if ref[:, c].std() > 0]
+            cors = [np.corrcoef(dev[:, c], ref[:, c])[0, 1] for c in cols]
+            assert min(cors) >= 0.9999, (k, min(cors))
+    finally:
+        handle.set_precision("mixed16")
 
 
-@pytest.mark.parametrize("k,maxit", [(4, 12), (10, 10), (32, 8), (48, 5)])
-def test_nmf_matches_oracle(handle, oracle, k, maxit):
-    """c_nmf (src/singlet.cpp:638-672) at a fixed iteration count."""
+@pytest.mark.parametrize("k,maxit,precision", [(4, 12, "mixed16"), (10, 10, "mixed16"), (32, 8, "mixed16"), (48, 5, "mixed16"),
+                                               (32, 8, "mixed16_always"), (48, 5, "mixed16_always")])
+def test_nmf_matches_oracle(handle, oracle, k, maxit, precision):
+    """c_nmf (src/singlet.cpp:638-672) at a fixed iteration count; default precision policy (FP32 operands at this size) and
+    16-bit staging forced."""
     from singlet_b200 import api, synth
 
     m, n = 900, 600
     A, At = _mk(m, n, 0.06, seed=100 + k)
     w0 = synth.w_init(k, m, seed=k)
-    dev = api.c_nmf(A, At, 0.0, maxit, False, 0.01, 0.02, 0.0, 0.0, 0, w0)
+    handle.set_precision(precision)
+    try:
+        dev = api.c_nmf(A, At, 0.0, maxit, False, 0.01, 0.02, 0.0, 0.0, 0, w0)
+    finally:
+        handle.set_precision("mixed16")
     ref = oracle.nmf(A, At, w0, tol=0.0, maxit=maxit, L1=(0.01, 0.02), L2=(0.0, 0.0))
     assert dev["iter"] == ref["iter"] == maxit
     perm = match_factors(ref["w"], dev["w"])
     assert min_factor_cor(ref["w"], dev["w"], perm) >= COR_MIN
     assert min_factor_cor(ref["h"], dev["h"], perm) >= COR_MIN
-    assert np.allclose(dev["d"][perm], ref["d"], rtol=5e-3)
+    assert np.allclose(dev["d"][perm], ref["d"], rtol=1e-3)
     assert abs(dev["tol"] - ref["tol"][-1]) <= 1e-3 * max(ref["tol"][-1], 1e-6) + 1e-7
     tr_dev = oracle.mse_train(A, dev["w"], dev["d"], dev["h"])
     tr_ref = oracle.mse_train(A, ref["w"], ref["d"], ref["h"])
@@ -254,7 +264,7 @@ def test_project_model_matches_oracle(handle, oracle):
     for arg in (w, np.ascontiguousarray(w.T)):
         dev = api.project_model(A, arg)
         assert min_factor_cor(ref["h"], dev["h"]) >= COR_MIN
-        assert np.allclose(dev["d"], ref["d"], rtol=5e-3)
+        assert np.allclose(dev["d"], ref["d"], rtol=1e-3)
     with pytest.raises(ValueError):
         api.project_model(A, np.ones((k, m + 1)))
 
@@ -324,7 +334,7 @@ def test_r_level_api_on_gpu(handle, oracle):
     ref = oracle.nmf(A, At, w0, tol=0.0, maxit=6)
     order = np.argsort(-ref["d"], kind="stable")
     assert min_factor_cor(ref["w"][order], model["w"].T) >= COR_MIN
-    assert np.allclose(model["d"], ref["d"][order], rtol=5e-3)
+    assert np.allclose(model["d"], ref["d"][order], rtol=1e-3)
 
     api.set_seed(123)
     df = api.cross_validate_nmf(A, [2, 3, 4], n_replicates=2, maxit=10, verbose=0, trace_test_mse=5)
@@ -358,7 +368,7 @@ def test_linked_nmf_matches_oracle(handle, oracle):
         ref = oracle.linked_nmf(A, At, w0, lh, lw, tol=0.0, maxit=6)
         assert dev["iter"] == 6
         assert min_factor_cor(ref["w"], dev["w"]) >= COR_MIN and min_factor_cor(ref["h"], dev["h"]) >= COR_MIN
-        assert np.allclose(dev["d"], ref["d"], rtol=5e-3)
+        assert np.allclose(dev["d"], ref["d"], rtol=1e-3)
         if lh.shape[1] == n:  # a linked-out factor stays exactly zero in that cell
             assert np.all(dev["h"][lh == 0] == 0)
 
@@ -389,7 +399,7 @@ def test_dense_variants_match_oracle(handle, oracle):
     dev = api.c_nmf_dense(D, Dt, 0.0, 6, False, 0.01, 0.01, 0.0, 0.0, 0, w0)
     ref = oracle.nmf_dense(D, Dt, w0, tol=0.0, maxit=6)
     assert min_factor_cor(ref["w"], dev["w"]) >= COR_MIN and min_factor_cor(ref["h"], dev["h"]) >= COR_MIN
-    assert np.allclose(dev["d"], ref["d"], rtol=5e-3)
+    assert np.allclose(dev["d"], ref["d"], rtol=1e-3)
     devm = api.c_ard_nmf_dense(D, Dt, 0.0, 5, False, 0.01, 0.0, 0, w0, 123, 10, 10.0, 2)
     refm = oracle.ard_nmf_dense(D, Dt, w0, 123, 10, tol=0.0, maxit=5, overfit_threshold=10.0, trace_test_mse=2)
     assert list(devm["iter"]) == list(refm["iter"]) and np.allclose(devm["test_mse"], refm["test_mse"], rtol=MSE_RTOL)
@@ -458,7 +468,7 @@ def test_pbmc3k_against_reference_goldens(handle, oracle):
     perm = match_factors(z["c1_w"].astype(np.float64), dev["w"])
     assert min_factor_cor(z["c1_w"].astype(np.float64), dev["w"], perm) >= COR_MIN
     assert min_factor_cor(z["c1_h"].astype(np.float64), dev["h"], perm) >= COR_MIN
-    assert np.allclose(dev["d"][perm], z["c1_d"], rtol=5e-3)
+    assert np.allclose(dev["d"][perm], z["c1_d"], rtol=1e-3)
     tr_dev = oracle.mse_train(A, dev["w"], dev["d"], dev["h"])
     tr_ref = oracle.mse_train(A, z["c1_w"].astype(np.float64), z["c1_d"], z["c1_h"].astype(np.float64))
     assert abs(tr_dev - tr_ref) <= MSE_RTOL * tr_ref
