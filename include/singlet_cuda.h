@@ -35,7 +35,9 @@ extern "C" {
 #define SGL_MAX_RANK 128
 
 /* dgCMatrix view: replaces Rcpp::SparseMatrix (inst/include/singlet.h:36-41). Read-only, caller
- * owned, must stay valid for the duration of the call only. */
+ * owned, must stay valid for the duration of the call only. A view may also be a COLUMN RANGE of a larger
+ * dgCMatrix, zero-copy: p points at the parent's p[c0] (so p[0] is the offset of the range's first non-zero)
+ * while i and x still point at the parent's arrays. */
 typedef struct sgl_csc {
     int64_t nrow, ncol;
     const int32_t* p; /* ncol + 1 */
@@ -254,6 +256,66 @@ int sgl_dev_update_masked(sgl_handle* h, const sgl_matrix* X, const sgl_mask* ma
  * which = 0: held-out entries (test); 1: the entries that are not held out (train, harness-defined). */
 int sgl_dev_mse(sgl_handle* h, const sgl_matrix* A, const sgl_mask* mask, const float* W, const double* d,
                 const float* H, int k, int which, double* loss_sum);
+
+/* ---- multi-GPU (csrc/multi.cu) ---------------------------------------------------
+ * The reference's chunk-list entry points (c_nmf_sparse_list src/singlet.cpp:715-743, c_ard_nmf_sparse_list :1162-1234,
+ * chunks and "distributed transpose" blocks built at R/cross_validate_nmf.R:37-50) map 1:1 onto GPUs: cells are sharded
+ * for the H update, genes for the W update; NCCL (bound at run time with dlopen) carries the k x m / k x n factor
+ * all-gathers, the reduce-scatter of the W-update right-hand sides and the all-reduces of Gram / row sums / loss.
+ * Shards are always the contiguous ranges of sgl_shard_bounds. */
+void sgl_shard_bounds(int64_t total, int world, int rank, int64_t* lo, int64_t* hi, int64_t* per);
+
+/* One rank of a GPU group: an sgl_handle plus an NCCL communicator on the handle's stream. */
+typedef struct sgl_comm sgl_comm;
+/* one-process-per-GPU jobs: rank 0 makes the 128-byte id, every rank receives it (any host transport) and joins */
+int sgl_comm_unique_id(void* id128);
+int sgl_comm_init_rank(sgl_handle* h, int device, int world, int rank, const void* id128, sgl_comm** out);
+int sgl_comm_destroy(sgl_comm* c);
+int sgl_comm_rank(const sgl_comm* c);
+int sgl_comm_world(const sgl_comm* c);
+sgl_handle* sgl_comm_handle(const sgl_comm* c);
+int64_t sgl_comm_collectives(const sgl_comm* c); /* NCCL calls issued so far */
+
+/* Device state of one sharded fit on one rank. masked == 0 (c_nmf): A_loc = this rank's cells (m x n_loc), At_loc = the
+ * transpose of that block (n_loc x m) or NULL to build it on the device. masked != 0 (c_ard_nmf): At_loc = this rank's
+ * genes over ALL cells (n_total x g_loc), required. w_init: k x m, identical on every rank. */
+typedef struct sgl_fit sgl_fit;
+int sgl_fit_create(sgl_comm* c, const sgl_matrix* A_loc, const sgl_matrix* At_loc, int64_t n_total, int k, const double* w_init,
+                   int masked, uint64_t seed, uint64_t inv_density, sgl_fit** out);
+/* one trip of src/singlet.cpp:648-659 (:1108-1114 when masked), collectives included; tol_out = 1 - cor(w, w_prev).
+ * stop_flag (optional, in/out): set to 1 on any rank to make EVERY rank leave with 1 (agreed through the all-reduce). */
+int sgl_fit_iterate(sgl_fit* f, double L1_w, double L1_h, double L2_w, double L2_h, double* tol_out, int* stop_flag);
+int sgl_fit_test_mse(sgl_fit* f, double* out);                            /* mse_test, all-reduced */
+int sgl_fit_download(sgl_fit* f, double* w, double* d, double* h_local);  /* k x m, k, k x n_loc; any may be NULL */
+int sgl_fit_shard(const sgl_fit* f, int64_t* c0, int64_t* c1, int64_t* g0, int64_t* g1);
+int sgl_fit_destroy(sgl_fit* f);
+
+/* Whole fits on one rank of a one-process-per-GPU job: every rank makes the same call with its shards; w (in/out), d, the
+ * iteration count and the trace are identical on all ranks, h_local is this rank's k x n_loc block. */
+int sgl_nmf_rank(sgl_comm* c, const sgl_matrix* A_loc, const sgl_matrix* At_loc, int64_t n_total, double tol, uint16_t maxit,
+                 double L1_w, double L1_h, double L2_w, double L2_h, int k, double* w, double* d, double* h_local,
+                 int32_t* iters_out, double* tol_out, const sgl_callbacks* cb);
+int sgl_ard_nmf_rank(sgl_comm* c, const sgl_matrix* A_loc, const sgl_matrix* At_loc, int64_t n_total, double tol, uint16_t maxit,
+                     double L1, double L2, int k, double* w, double* d, double* h_local, uint64_t seed, uint64_t inv_density,
+                     double overfit_threshold, uint16_t trace_test_mse, sgl_trace* trace, const sgl_callbacks* cb);
+
+/* All devices of ONE process (what an R session is): ncclCommInitAll, one host thread per device, callbacks on the
+ * calling thread only. devices == NULL: 0 .. n_devices - 1. */
+typedef struct sgl_multi sgl_multi;
+int sgl_multi_create(int n_devices, const int* devices, sgl_multi** out);
+int sgl_multi_destroy(sgl_multi* mg);
+int sgl_multi_size(const sgl_multi* mg);
+sgl_comm* sgl_multi_rank(const sgl_multi* mg, int rank);
+int sgl_multi_set_precision(sgl_multi* mg, int mode);
+/* c_nmf_sparse_list / c_ard_nmf_sparse_list over the devices: the chunk lists are re-cut into one shard per device without
+ * copying (column-range views). Same arguments and results as sgl_nmf / sgl_ard_nmf; sgl_multi_nmf ignores At (every
+ * device transposes its own cell block), sgl_multi_ard_nmf needs the gene-block list. */
+int sgl_multi_nmf(sgl_multi* mg, const sgl_csc* A, int nA, const sgl_csc* At, int nAt, double tol, uint16_t maxit, double L1_w,
+                  double L1_h, double L2_w, double L2_h, int k, double* w, double* d, double* h_out, int32_t* iters_out,
+                  double* tol_out, const sgl_callbacks* cb);
+int sgl_multi_ard_nmf(sgl_multi* mg, const sgl_csc* A, int nA, const sgl_csc* At, int nAt, double tol, uint16_t maxit, double L1,
+                      double L2, int k, double* w, double* d, double* h_out, uint64_t seed, uint64_t inv_density,
+                      double overfit_threshold, uint16_t trace_test_mse, sgl_trace* trace, const sgl_callbacks* cb);
 
 #ifdef __cplusplus
 }

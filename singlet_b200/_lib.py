@@ -105,6 +105,31 @@ SYMBOLS = [
     ("sgl_mask_column", _i64, [_vp, _vp, _i64, _vp, _i64]),
     ("sgl_dev_update_masked", _i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _dbl, _dbl, _vp]),
     ("sgl_dev_mse", _i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    # multi-GPU (csrc/multi.cu)
+    ("sgl_shard_bounds", None, [_i64, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    ("sgl_comm_unique_id", _i32, [_vp]),
+    ("sgl_comm_init_rank", _i32, [_vp, _i32, _i32, _i32, _vp, C.POINTER(_vp)]),
+    ("sgl_comm_destroy", _i32, [_vp]),
+    ("sgl_comm_rank", _i32, [_vp]),
+    ("sgl_comm_world", _i32, [_vp]),
+    ("sgl_comm_handle", _vp, [_vp]),
+    ("sgl_comm_collectives", _i64, [_vp]),
+    ("sgl_fit_create", _i32, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _u64, _u64, C.POINTER(_vp)]),
+    ("sgl_fit_iterate", _i32, [_vp, _dbl, _dbl, _dbl, _dbl, C.POINTER(_dbl), C.POINTER(_i32)]),
+    ("sgl_fit_test_mse", _i32, [_vp, C.POINTER(_dbl)]),
+    ("sgl_fit_download", _i32, [_vp, _vp, _vp, _vp]),
+    ("sgl_fit_shard", _i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    ("sgl_fit_destroy", _i32, [_vp]),
+    ("sgl_nmf_rank", _i32, [_vp, _vp, _vp, _i64, _dbl, _u16, _dbl, _dbl, _dbl, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("sgl_ard_nmf_rank", _i32, [_vp, _vp, _vp, _i64, _dbl, _u16, _dbl, _dbl, _i32, _vp, _vp, _vp, _u64, _u64, _dbl, _u16, _vp, _vp]),
+    ("sgl_multi_create", _i32, [_i32, _vp, C.POINTER(_vp)]),
+    ("sgl_multi_destroy", _i32, [_vp]),
+    ("sgl_multi_size", _i32, [_vp]),
+    ("sgl_multi_rank", _vp, [_vp, _i32]),
+    ("sgl_multi_set_precision", _i32, [_vp, _i32]),
+    ("sgl_multi_nmf", _i32, [_vp, _vp, _i32, _vp, _i32, _dbl, _u16, _dbl, _dbl, _dbl, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("sgl_multi_ard_nmf", _i32, [_vp, _vp, _i32, _vp, _i32, _dbl, _u16, _dbl, _dbl, _i32, _vp, _vp, _vp, _u64, _u64, _dbl, _u16,
+                                 _vp, _vp]),
 ]
 
 

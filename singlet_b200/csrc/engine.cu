@@ -273,17 +273,23 @@ static inline uint64_t hash_piece_mix(uint64_t hb, int chunk, int64_t piece) {
 }
 static inline uint64_t hash_pointers(const sgl_csc& c, int chunk) {  // the column pointers of one chunk
     uint64_t h = splitmix64(0xC0FFEEull ^ (uint64_t)chunk);
-    for (int64_t t = 0; t <= c.ncol; ++t) h = (h ^ (uint64_t)(uint32_t)c.p[t]) * 0x9E3779B97F4A7C15ull, h ^= h >> 31;
+    for (int64_t t = 0; t <= c.ncol; ++t) h = (h ^ (uint64_t)(uint32_t)(c.p[t] - c.p[0])) * 0x9E3779B97F4A7C15ull, h ^= h >> 31;
     return splitmix64(h ^ ((uint64_t)c.nrow << 1) ^ ((uint64_t)c.ncol << 33));
 }
 static constexpr int64_t HASH_PIECE = (int64_t)1 << 19;  // == sgl_handle::STAGE_RECORDS (the packing granularity)
+
+// A chunk may be a COLUMN RANGE of a larger dgCMatrix viewed in place: p points into the parent's p, so p[0] is the
+// offset of the range's first non-zero inside i / x (which still point at the parent's arrays).
+static inline int64_t chunk_base(const sgl_csc& c) { return (int64_t)c.p[0]; }
+static inline int64_t chunk_nnz(const sgl_csc& c) { return (int64_t)c.p[c.ncol] - (int64_t)c.p[0]; }
 
 static int validate_chunk_args(const sgl_csc* c, int n) {
     if (!c || n < 1) return fail(SGL_EINVAL, "matrix: empty chunk list");
     for (int q = 0; q < n; ++q) {
         if (!c[q].p) return fail(SGL_EINVAL, "matrix: NULL column pointers in chunk %d", q);
         if (c[q].ncol < 0 || c[q].nrow < 1) return fail(SGL_EINVAL, "matrix: bad dimensions in chunk %d", q);
-        if (c[q].p[c[q].ncol] > 0 && (!c[q].i || !c[q].x)) return fail(SGL_EINVAL, "matrix: NULL slot in chunk %d", q);
+        if (c[q].p[0] < 0 || c[q].p[c[q].ncol] < c[q].p[0]) return fail(SGL_EINVAL, "matrix: bad column pointers in chunk %d", q);
+        if (chunk_nnz(c[q]) > 0 && (!c[q].i || !c[q].x)) return fail(SGL_EINVAL, "matrix: NULL slot in chunk %d", q);
     }
     return SGL_OK;
 }
@@ -293,7 +299,7 @@ static uint64_t content_hash_chunks(const sgl_csc* c, int n) {
     std::vector<std::pair<int, int64_t>> pieces;
     for (int q = 0; q < n; ++q) {
         total ^= hash_pointers(c[q], q);
-        const int64_t nnz = c[q].p[c[q].ncol];
+        const int64_t nnz = chunk_nnz(c[q]);
         for (int64_t pc = 0; pc * HASH_PIECE < nnz; ++pc) pieces.emplace_back(q, pc);
     }
     unsigned hw = std::thread::hardware_concurrency();
@@ -304,9 +310,9 @@ static uint64_t content_hash_chunks(const sgl_csc* c, int n) {
         uint64_t a = 0;
         for (size_t e = (size_t)wid; e < pieces.size(); e += (size_t)nt) {
             const int q = pieces[e].first;
-            const int64_t pc = pieces[e].second, nnz = c[q].p[c[q].ncol], o = pc * HASH_PIECE;
+            const int64_t pc = pieces[e].second, nnz = chunk_nnz(c[q]), o = pc * HASH_PIECE, base = chunk_base(c[q]);
             const int64_t len = (nnz - o) < HASH_PIECE ? (nnz - o) : HASH_PIECE;
-            a ^= hash_piece_mix(hash_block(c[q].i + o, c[q].x + o, len), q, pc);
+            a ^= hash_piece_mix(hash_block(c[q].i + base + o, c[q].x + base + o, len), q, pc);
         }
         acc[(size_t)wid] = a;
     };
@@ -330,14 +336,15 @@ static uint64_t fingerprint_chunks(const sgl_csc* c, int n) {
         mix((uint64_t)(uintptr_t)c[q].x);
         mix((uint64_t)c[q].nrow);
         mix((uint64_t)c[q].ncol);
-        const int64_t nnz = c[q].p[c[q].ncol];
+        const int64_t nnz = chunk_nnz(c[q]), base = chunk_base(c[q]);
         mix((uint64_t)nnz);
+        mix((uint64_t)base);
         // sample of the contents: a cheap first filter (a match is confirmed by content_hash_chunks)
         const int64_t step = nnz > 4096 ? nnz / 4096 : 1;
         for (int64_t t = 0; t < nnz; t += step) {
             uint64_t bits;
-            std::memcpy(&bits, &c[q].x[t], 8);
-            mix(bits ^ ((uint64_t)(uint32_t)c[q].i[t] << 1));
+            std::memcpy(&bits, &c[q].x[base + t], 8);
+            mix(bits ^ ((uint64_t)(uint32_t)c[q].i[base + t] << 1));
         }
         const int64_t cstep = c[q].ncol > 1024 ? c[q].ncol / 1024 : 1;
         for (int64_t t = 0; t <= c[q].ncol; t += cstep) mix((uint64_t)c[q].p[t]);
@@ -350,14 +357,14 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
     int64_t nrow = chunks[0].nrow, ncol = 0, nnz = 0;
     for (int q = 0; q < n_chunks; ++q) {
         const sgl_csc& c = chunks[q];
-        if (!c.p || (c.p[c.ncol] > 0 && (!c.i || !c.x))) return fail(SGL_EINVAL, "matrix upload: NULL slot in chunk %d", q);
+        if (!c.p || c.ncol < 0 || (chunk_nnz(c) > 0 && (!c.i || !c.x))) return fail(SGL_EINVAL, "matrix upload: NULL slot in chunk %d", q);
         if (c.nrow != nrow) return fail(SGL_EINVAL, "matrix upload: chunk %d has %lld rows, expected %lld", q, (long long)c.nrow, (long long)nrow);
         if (c.nrow < 1 || c.nrow > 0x7fffffffLL || c.ncol < 0) return fail(SGL_EINVAL, "matrix upload: bad dimensions in chunk %d", q);
-        if (c.p[0] != 0) return fail(SGL_EINVAL, "matrix upload: p[0] != 0 in chunk %d", q);
+        if (c.p[0] < 0) return fail(SGL_EINVAL, "matrix upload: p[0] < 0 in chunk %d", q);
         for (int64_t t = 0; t < c.ncol; ++t)
             if (c.p[t + 1] < c.p[t]) return fail(SGL_EINVAL, "matrix upload: p not monotone in chunk %d", q);
         ncol += c.ncol;
-        nnz += c.p[c.ncol];
+        nnz += chunk_nnz(c);
     }
     SGL_TRY(set_device(h));
     sgl_matrix* m = new sgl_matrix();
@@ -402,10 +409,10 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
     static_assert(HASH_PIECE == (int64_t)sgl_handle::STAGE_RECORDS, "hash pieces must be the packing pieces");
     for (int q = 0; q < n_chunks && rc == SGL_OK; ++q) {
         const sgl_csc& c = chunks[q];
-        const int64_t cn = c.p[c.ncol];
+        const int64_t cn = chunk_nnz(c), cbase = chunk_base(c);
         cudaMemcpyAsync(d_p, c.p, sizeof(int32_t) * (size_t)(c.ncol + 1), cudaMemcpyHostToDevice, h->stream);
         const int last = (q == n_chunks - 1) ? 1 : 0;
-        colptr_from_p32_kernel<<<blocks_for(c.ncol + 1, 256), 256, 0, h->stream>>>(d_p, c.ncol, nnz_off, m->colptr + col_off, last);
+        colptr_from_p32_kernel<<<blocks_for(c.ncol + 1, 256), 256, 0, h->stream>>>(d_p, c.ncol, nnz_off - cbase, m->colptr + col_off, last);
         ++h->launches;
         cudaStreamSynchronize(h->stream);  // d_p is reused by the next chunk
         const int64_t PIECE = (int64_t)sgl_handle::STAGE_RECORDS;
@@ -425,8 +432,8 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
                 const int64_t len = (cn - o) < PIECE ? (cn - o) : PIECE;
                 if (done_pieces >= 2) cudaEventSynchronize(h->stage_ev[wid][use]);  // buffer free again
                 uint2* buf = h->stage[wid][use];
-                const int32_t* si = c.i + o;
-                const double* sx = c.x + o;
+                const int32_t* si = c.i + cbase + o;
+                const double* sx = c.x + cbase + o;
                 worker_hash[(size_t)wid] ^= hash_piece_mix(hash_block(si, sx, len), q, pc);
                 for (int64_t t = 0; t < len; ++t) {
                     const float v = (float)sx[t];
