@@ -48,6 +48,7 @@ CONFIGS = {
     "c5": dict(m=35000, n=4000000, density=0.03, k=64, name="synthetic 35k genes x 4M cells, 3% density, k=64 (atlas scale)"),
     # smaller stand-ins for quick checks (never the default)
     "c5shard": dict(m=35000, n=500000, density=0.03, k=64, name="one eighth of config 5 (35k x 500k, 3%, k=64; tuning only)"),
+    "c3r8": dict(m=30000, n=125000, density=0.05, k=32, name="one rank's eighth of config 2's cells (30k x 125k; profiling only)"),
     "mid": dict(m=30000, n=100000, density=0.05, k=32, name="MID 30k x 100k (not a bench config)"),
     "mini": dict(m=3000, n=20000, density=0.05, k=32, name="MINI 3k x 20k (not a bench config)"),
     "c4shape": dict(m=20000, n=250000, density=0.08, k=16, name="synthetic 20k x 250k, 8% density, k=16 (shape of config 4)"),
@@ -261,11 +262,14 @@ def main():
     import torch.distributed as dist
 
     from singlet_b200 import synth
-    from singlet_b200.sharded import CudaBackend, ShardedNMF, shard_bounds
+    from singlet_b200.multi import RankComm, RankFit
+    from singlet_b200.sharded import CudaBackend, shard_bounds
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    if world > 1:  # the ranks share the host cores: cap every rank's upload packing threads
+        os.environ.setdefault("SGL_UPLOAD_THREADS", str(max(2, (os.cpu_count() or 8) // world)))
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -282,8 +286,10 @@ def main():
     be.synchronize()
     t_gen = time.perf_counter() - t_gen
     nnz_A, nnz_At = be.matrix_info(A_sh)[2], be.matrix_info(At_sh)[2]
-    fit = ShardedNMF(be, m, n, k, A_sh, At_sh, rank, world, group, layout="B")
-    fit.set_w(synth.w_init(k, m))
+    # the sharded fit and every collective of it live in the C++ library (csrc/multi.cu: sgl_comm / sgl_fit, NCCL on the
+    # library's stream); torch.distributed only hands the NCCL unique id round and carries the timing reductions below
+    comm = RankComm(be._h, local_rank, world, rank, group)
+    fit = RankFit(comm, A_sh, At_sh, n, k, synth.w_init(k, m))
 
     def barrier():
         torch.cuda.synchronize()
@@ -292,7 +298,7 @@ def main():
             torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        fit.iteration(L1, L1, L2, L2)
+        fit.iterate(L1, L1, L2, L2)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -304,14 +310,17 @@ def main():
     barrier()
     ev0.record()
     tol = None
+    coll0 = comm.collectives()
     for _ in range(args.steps):
-        tol = fit.iteration(L1, L1, L2, L2)
+        tol = fit.iterate(L1, L1, L2, L2)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     prof = be.profile_read()
     be.profile(False)
     launches = be.launch_count() - launches0
+    n_coll = comm.collectives() - coll0
+    fit.close()
     clocks = sampler.stop() if sampler else None
     stats = torch.tensor([ms, float(launches), float(nnz_A), float(nnz_At), prof["spmm"][0], float(prof["spmm"][2]),
                           prof["nnls"][0], prof["gram"][0]], dtype=torch.float64, device=be.device)
@@ -346,7 +355,8 @@ def main():
                              "MIXED16, the default)" if mixed else "FP32 operands and accumulation (SGL_PRECISION=fp32)"),
                "data": "synthetic (device-generated, bit-identical to singlet_b200/synth.py)",
                "config": dict(base_cfg, nnz=nnz_total, generate_s=round(t_gen, 3), final_tol=tol),
-               "gpu_launches": total_launches, "clocks": clocks,
+               "gpu_launches": total_launches, "nccl_collectives_per_step_per_rank": n_coll / args.steps, "clocks": clocks,
+               "driver": "csrc/multi.cu sgl_fit_iterate through the C ABI (one process per GPU, NCCL issued by the library)",
                "roofline": {"bound": "hbm", "kernel": kernel + " (mean of the H-update and W-update launches, rank 0)",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": ncu_traffic(args.config, world, kernel),
@@ -364,7 +374,7 @@ def main():
             if world == 1:
                 e2e = e2e_leg(be, cfg, args.steps, A_sh, At_sh)
             else:
-                e2e = e2e_leg_sharded(be, cfg, args.steps, A_sh, At_sh, rank, world, group)
+                e2e = e2e_leg_sharded(be, comm, cfg, args.steps, A_sh, rank, world)
         except MemoryError as ex:
             e2e = {"value": None, "unit": "iterations/s", "error": f"host memory: {ex}"}
     if rank == 0:
@@ -374,6 +384,7 @@ def main():
             # bounded: ~10-30 s of CPU work (two warm iterations at 12,800 and 38,400 cells)
             cells = args.cpu_sample_cells if args.cpu_sample_cells > 0 else min(n, 38400)
             out["cpu_baseline"] = cpu_reference_leg(cfg, 2, cells)
+    comm.close()
     be.close()
     be = None
     if rank == 0:
@@ -514,42 +525,49 @@ def planted_counts(m, n, rank, density, seed):
     return X
 
 
-def e2e_leg_sharded(be, cfg, steps, A_dev, At_dev, rank, world, group):
-    """N > 1: every rank starts from HOST dgCMatrix shards (its cells, and the transpose of that block), uploads
-    them, runs `steps` iterations of the sharded fit and downloads the replicated model. Max over ranks."""
+def e2e_leg_sharded(be, comm, cfg, steps, A_dev, rank, world):
+    """N > 1: every rank starts from its HOST dgCMatrix cell shard and makes ONE call of the per-rank C ABI entry point
+    sgl_nmf_rank: upload, device transpose, `steps` iterations with NCCL inside the library, download of w, d and of the
+    rank's own block of h. Max over ranks."""
+    import ctypes as C
+
     import scipy.sparse as sp
     import torch
     import torch.distributed as dist
 
-    from singlet_b200 import synth
-    from singlet_b200.sharded import ShardedNMF, shard_bounds
+    from singlet_b200 import _lib, synth
+    from singlet_b200.sharded import shard_bounds
 
     m, n, k = cfg["m"], cfg["n"], cfg["k"]
     c0, c1, _ = shard_bounds(n, world, rank)
     pA = be.matrix_to_host(A_dev)
     A = sp.csc_matrix((pA[2], pA[1], pA[0]), shape=(m, c1 - c0))
     A.has_sorted_indices = True
-    w0 = synth.w_init(k, m)
+    w = np.array(synth.w_init(k, m), order="F")
+    d, h_loc = np.zeros(k), np.zeros((k, c1 - c0), order="F")
+    iters = C.c_int32(0)
+    lib = be.lib
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
-    hA = be.upload(A)  # the transpose of the local block is built on the device (sgl_matrix_transpose)
-    fit = ShardedNMF(be, m, n, k, hA, None, rank, world, group, layout="B")
-    fit.set_w(w0)
-    for _ in range(steps):
-        fit.iteration(L1, L1, L2, L2)
-    w, d, h = fit.factors_to_host()
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=be.device)
+    arr, na, keep = _lib.chunks_to_c([A])
+    hA = C.c_void_p()
+    _lib.check(lib.sgl_matrix_upload(be._h, arr, na, C.byref(hA)))
+    _lib.check(lib.sgl_nmf_rank(comm._c, hA, None, n, 0.0, steps, L1, L1, L2, L2, k, w.ctypes.data, d.ctypes.data, h_loc.ctypes.data,
+                                C.addressof(iters), None, None))
+    sec_local = time.perf_counter() - t0
+    lib.sgl_matrix_free(be._h, hA)
+    dt = torch.tensor([sec_local], dtype=torch.float64, device=be.device)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    h2d = torch.tensor([float(A.data.nbytes + A.indices.nbytes + A.indptr.nbytes + w0.nbytes)], dtype=torch.float64, device=be.device)
+    h2d = torch.tensor([float(A.data.nbytes + A.indices.nbytes + A.indptr.nbytes + w.nbytes)], dtype=torch.float64, device=be.device)
     dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
-    d2h = float(world) * (w.nbytes + h.nbytes + d.nbytes + steps * 40)
+    d2h = float(world) * (w.nbytes + d.nbytes + steps * 40) + 8.0 * k * n
     sec = float(dt[0])
+    assert iters.value == steps
     return {"value": steps / sec, "unit": "iterations/s", "h2d_bytes_per_step": float(h2d[0]) / steps, "d2h_bytes_per_step": d2h / steps,
-            "seconds_total": sec, "iterations": steps,
-            "note": "sharded public API (singlet_b200.sharded): every rank uploads its host dgCMatrix cell shard (FP64) and transposes "
-                    "it on the device, K iterations, replicated w/d/h downloaded on every rank; max over ranks"}
+            "seconds_total": sec, "iterations": steps, "call": "sgl_matrix_upload + sgl_nmf_rank per rank (include/singlet_cuda.h)",
+            "note": "every rank uploads its host dgCMatrix cell shard (FP64), transposes it on the device, runs K iterations and downloads "
+                    "w, d and its own block of h; max over ranks"}
 
 
 def e2e_leg(be, cfg, steps, A_dev, At_dev):

@@ -906,14 +906,15 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
             SGL_CUDA(cudaMemcpyToSymbolAsync(c_gram, h->gram_f.p, sizeof(float) * KPV * KPV, 0, cudaMemcpyDeviceToDevice, h->stream));
             SGL_CUDA(cudaMemcpyToSymbolAsync(c_inv_diag, h->inv_diag.p, sizeof(float) * KPV, 0, cudaMemcpyDeviceToDevice, h->stream));
             switch (KPV) {
-#define NNLS_LAUNCH(KPC, NTC, NCLC)                                                                                  \
+#define NNLS_LAUNCH(KPC, NTC, NCLC, ...)                                                                             \
     {                                                                                                               \
         static int occ = 0;                                                                                         \
-        if (!occ && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nnls_cols_kernel<KPC, NTC, NCLC>, NTC, 0) != cudaSuccess) occ = 1; \
+        if (!occ && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nnls_cols_kernel<KPC, NTC, NCLC __VA_ARGS__>, NTC, 0) != cudaSuccess) occ = 1; \
         int64_t ctas = (int64_t)h->sm_count * (occ > 0 ? occ : 1);                                                  \
         const int64_t want = (ncol + (NTC) * (NCLC) - 1) / ((NTC) * (NCLC));                                      \
-        if (ctas > want) ctas = want;                                                                               \
-        nnls_cols_kernel<KPC, NTC, NCLC><<<(unsigned)ctas, NTC, 0, h->stream>>>(                                      \
+        /* fewer CTAs than fit: keep the same number on every SM (the lanes claim columns one by one) */           \
+        if (ctas > want) ctas = want <= h->sm_count ? want : (want + h->sm_count - 1) / h->sm_count * h->sm_count;  \
+        nnls_cols_kernel<KPC, NTC, NCLC __VA_ARGS__><<<(unsigned)ctas, NTC, 0, h->stream>>>(                          \
             Bparts, splits, F_out, colptr, ncol, k, (float)L1, (float)L2, h->workctr.p, dbg_stats ? h->workctr.p + 2 : nullptr); \
     }
 #define NNLS_CASE(KPC)                                                                                              \
@@ -921,7 +922,20 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
         if (ncol >= (int64_t)h->sm_count * NnlsCfg<KPC>::THREADS * 2) NNLS_LAUNCH(KPC, NnlsCfg<KPC>::THREADS, NnlsCfg<KPC>::NCL) \
         else NNLS_LAUNCH(KPC, 32, 1)                                                                                \
         break;
-                NNLS_CASE(4) NNLS_CASE(8) NNLS_CASE(16) NNLS_CASE(32) NNLS_CASE(64)
+                NNLS_CASE(4) NNLS_CASE(8) NNLS_CASE(16) NNLS_CASE(64)
+                case 32: {
+                    // (three columns per lane -- 168 registers, 1152 columns in flight per SM -- measured slower: 5.96 vs 4.94 ms
+                    //  for 10^6 columns; profiles/r2_nnls.md)
+                    // (a 128-register build that keeps 4 CTAs per SM resident, so that one eighth of the headline config's cells
+                    //  -- 125,000 columns -- makes ONE round of the grid, and a sweep that skips warp-empty slots were measured too:
+                    //  no gain / slower; the kernel is FP32-pipe bound either way -- profiles/r2_nnls.md)
+                    // (tried for the 125,000-column case of a rank on 8 GPUs, 1.1 rounds of the grid: a 128-register build with 4 CTAs
+                    //  or 16 one-warp CTAs per SM so that ONE round suffices, three columns per lane, and a sweep that skips warp-empty
+                    //  slots. None beat 0.83 ms: the 128-register code is ~45 % slower per column -- profiles/r2_nnls.md)
+                    if (false) {}
+                    else if (ncol >= (int64_t)h->sm_count * 128 * 2) NNLS_LAUNCH(32, 128, 2)
+                    else NNLS_LAUNCH(32, 32, 1)
+                } break;
                 default: break;
 #undef NNLS_LAUNCH
 #undef NNLS_CASE

@@ -95,8 +95,10 @@ __constant__ float c_inv_diag[64];
 // lane solves which column. Row sums are taken afterwards by rowsum_partial_kernel.
 // NT threads per CTA, NCL columns per lane: <THREADS, 2> for large column counts; <32, 1> when there are
 // too few columns to fill the chip otherwise (e.g. a gene shard of the W update on 8 GPUs).
-template <int KP, int NT, int NCL>
-__global__ void __launch_bounds__(NT, (NT == 32) ? 8 : NnlsCfg<KP>::MIN_CTAS)
+// MINB: CTAs per SM the register allocation must allow (default: 3 CTAs of 128 threads -- <= 170 registers, the fastest
+// code when the columns make many rounds of the persistent grid -- or 8 of 32 threads).
+template <int KP, int NT, int NCL, int MINB = ((NT == 32) ? 8 : NnlsCfg<KP>::MIN_CTAS)>
+__global__ void __launch_bounds__(NT, MINB)
 nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
                  int splits, float* __restrict__ X,  // [ncol][KP] warm start in / solution out
                  const int64_t* __restrict__ colptr, int64_t ncol, int k, float L1, float L2,

@@ -42,7 +42,9 @@ def test_multi_nmf_equals_single_gpu_fit(handle, oracle, world):
             assert np.array_equal(dev["w"], one["w"]) and np.array_equal(dev["h"], one["h"]) and np.array_equal(dev["d"], one["d"])
         else:
             assert sum(mg.collectives()) > 0
-            assert np.allclose(dev["w"], one["w"], rtol=2e-4, atol=1e-9) and np.allclose(dev["h"], one["h"], rtol=2e-4, atol=1e-9)
+            # FP32 sums are formed in another order (partial Grams / right-hand sides per rank): equal to ~1e-4 of the largest entry
+            for nm in ("w", "h"):
+                assert np.abs(dev[nm] - one[nm]).max() <= 2e-4 * np.abs(one[nm]).max(), nm
             assert np.allclose(dev["d"], one["d"], rtol=1e-5)
     finally:
         mg.close()
@@ -75,7 +77,8 @@ def test_multi_ard_nmf_equals_single_gpu_fit(handle, oracle, world):
         mg.close()
     assert list(dev["iter"]) == list(one["iter"])
     assert np.allclose(dev["test_mse"], one["test_mse"], rtol=1e-6)
-    assert np.allclose(dev["w"], one["w"], rtol=2e-4, atol=1e-9) and np.allclose(dev["h"], one["h"], rtol=2e-4, atol=1e-9)
+    for nm in ("w", "h"):
+        assert np.abs(dev[nm] - one[nm]).max() <= 2e-4 * np.abs(one[nm]).max(), nm
     ref = oracle.ard_nmf(A, At, w0, 999, 20, tol=0.0, maxit=5, L1=0.01, L2=0.0, overfit_threshold=10.0, trace_test_mse=2)
     assert list(dev["iter"]) == list(ref["iter"]) and np.allclose(dev["test_mse"], ref["test_mse"], rtol=1e-4)
 
