@@ -257,6 +257,22 @@ int sgl_dev_update_masked(sgl_handle* h, const sgl_matrix* X, const sgl_mask* ma
 int sgl_dev_mse(sgl_handle* h, const sgl_matrix* A, const sgl_mask* mask, const float* W, const double* d,
                 const float* H, int k, int which, double* loss_sum);
 
+/* ---- IVSparse wire formats (csrc/ivsparse.cpp) -------------------------------
+ * Host-side codec for the file images of the reference's vendored IVSparse library: IVCSC (compression level 3,
+ * inst/include/src/IVCSC/IVCSC_Methods.hpp:72-95, IVCSC_Private_Methods.hpp:128-299) and VCSC (level 2,
+ * inst/include/src/VCSC/VCSC_Methods.hpp:77-109), as written by write_IVCSC / save_IVSparse / build_IVCSC2 and read by
+ * read_IVSparse / run_nmf_on_sparsematrix_list (src/singlet.cpp:783-995). `image` is the whole file in memory. */
+int sgl_ivsparse_info(const void* image, uint64_t bytes, int32_t* level, int64_t* nrow, int64_t* ncol, int64_t* nnz,
+                      int32_t* value_bytes);
+/* Columns [col0, col0 + ncol) as dgCMatrix slots (p has ncol + 1 entries, rows ascending within a column). Returns the
+ * non-zeros of the range; with i = x = NULL only p is filled (sizing call). A range must hold < 2^31 non-zeros: decode an
+ * atlas-scale file as a list of column chunks and hand that list to sgl_nmf / sgl_multi_nmf. */
+int64_t sgl_ivsparse_decode(const void* image, uint64_t bytes, int64_t col0, int64_t ncol, int32_t* p, int32_t* i, double* x,
+                            int64_t capacity);
+/* The image the reference's IVCSC (level 3) / VCSC (level 2) type writes for this chunk list (float values, 8-byte index
+ * type in the metadata). Returns its size; writes it when out != NULL. */
+int64_t sgl_ivsparse_encode(const sgl_csc* chunks, int n_chunks, int level, void* out, uint64_t capacity);
+
 /* ---- multi-GPU (csrc/multi.cu) ---------------------------------------------------
  * The reference's chunk-list entry points (c_nmf_sparse_list src/singlet.cpp:715-743, c_ard_nmf_sparse_list :1162-1234,
  * chunks and "distributed transpose" blocks built at R/cross_validate_nmf.R:37-50) map 1:1 onto GPUs: cells are sharded

@@ -105,6 +105,10 @@ SYMBOLS = [
     ("sgl_mask_column", _i64, [_vp, _vp, _i64, _vp, _i64]),
     ("sgl_dev_update_masked", _i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _dbl, _dbl, _vp]),
     ("sgl_dev_mse", _i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    # IVSparse wire formats (csrc/ivsparse.cpp)
+    ("sgl_ivsparse_info", _i32, [_vp, _u64, C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
+    ("sgl_ivsparse_decode", _i64, [_vp, _u64, _i64, _i64, _vp, _vp, _vp, _i64]),
+    ("sgl_ivsparse_encode", _i64, [_vp, _i32, _i32, _vp, _u64]),
     # multi-GPU (csrc/multi.cu)
     ("sgl_shard_bounds", None, [_i64, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     ("sgl_comm_unique_id", _i32, [_vp]),

@@ -411,20 +411,22 @@ def _sort_model(model, rank):
 def run_nmf(A, rank, tol=1e-4, maxit=100, verbose=True, L1=0.01, L2=0, threads=0, compression_level=3, rng=None,
             handle: Handle | None = None, device_transpose: bool = True):
     """``run_nmf`` (reference R/run_nmf.R:18-77). Returns ``{"w": m x k, "d": k, "h": k x n}`` sorted by
-    ``d``. A list input is treated as column chunks and routed to ``c_nmf_sparse_list`` with a
-    distributed transpose (the reference sends lists to its IVSparse development path, which is out
-    of scope: SURVEY.md 2.1). ``device_transpose`` (default): ``t(A)`` of R/run_nmf.R:40 is built on the device
-    (``sgl_matrix_transpose``, bit-identical records) instead of on the host."""
+    ``d``. A list input goes where the reference sends it (R/run_nmf.R:21-35): to
+    ``run_nmf_on_sparsematrix_list`` (``singlet_b200.ivsparse``) -- the chunks packed as one IVCSC / VCSC
+    (``compression_level`` 2) image with float values, plain ALS with NO penalties (the reference does not forward
+    L1/L2 on this path). For penalised fits of a chunk list call ``c_nmf_sparse_list``. ``device_transpose`` (default):
+    ``t(A)`` of R/run_nmf.R:40 is built on the device (``sgl_matrix_transpose``, bit-identical records) instead of on the host."""
     r = _rng(rng)
     L1 = (L1, L1) if np.isscalar(L1) else (L1[0], L1[1] if len(L1) == 2 else L1[0])
     L2 = (L2, L2) if np.isscalar(L2) else (L2[0], L2[1] if len(L2) == 2 else L2[0])
     if isinstance(A, (list, tuple)):
+        from .ivsparse import run_nmf_on_sparsematrix_list
+
         A = _as_csc(list(A))
         if len({a.shape[0] for a in A}) != 1:
             raise ValueError("number of rows in all provided 'A' matrices are not identical")
-        At = _distributed_transpose(A) if _host_transpose_needed(A, device_transpose) else None
         w_init = r.matrix_runif(rank, A[0].shape[0])
-        model = c_nmf_sparse_list(A, At, tol, maxit, verbose, L1[0], L2[0], threads, w_init, handle)
+        model = run_nmf_on_sparsematrix_list(A, tol, maxit, verbose, threads, w_init, compression_level == 2, handle=handle)
     else:
         if verbose:
             print("running with sparse optimization")
