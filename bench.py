@@ -49,6 +49,8 @@ CONFIGS = {
     # smaller stand-ins for quick checks (never the default)
     "c5shard": dict(m=35000, n=500000, density=0.03, k=64, name="one eighth of config 5 (35k x 500k, 3%, k=64; tuning only)"),
     "c3r8": dict(m=30000, n=125000, density=0.05, k=32, name="one rank's eighth of config 2's cells (30k x 125k; profiling only)"),
+    "c3r4": dict(m=30000, n=250000, density=0.05, k=32, name="one rank's quarter of config 2's cells (30k x 250k; profiling only)"),
+    "c3r2": dict(m=30000, n=500000, density=0.05, k=32, name="one rank's half of config 2's cells (30k x 500k; profiling only)"),
     "mid": dict(m=30000, n=100000, density=0.05, k=32, name="MID 30k x 100k (not a bench config)"),
     "mini": dict(m=3000, n=20000, density=0.05, k=32, name="MINI 3k x 20k (not a bench config)"),
     "c4shape": dict(m=20000, n=250000, density=0.08, k=16, name="synthetic 20k x 250k, 8% density, k=16 (shape of config 4)"),

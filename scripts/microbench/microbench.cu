@@ -4,6 +4,9 @@
 //      8-lane phase in the same / opposite halves of the 128-byte bank line, and 128-byte rows (FP32 operand)
 //   2. FP32-accumulate math on a 16-bit operand: HADD2.F32 + FFMA2 against FHFMA (fma.rn.f32.f16) against FFMA2 alone
 //   3. tensor memory as a gather table: tcgen05.ld.32x32b.x1 with a data-dependent column
+//   4. the masked solver's Gram correction G_M = sum_r f_r f_r^T (k = 32) per column: the FP32 rank-1 update of
+//      nnls_masked_sub_kernel (8 lanes per column, 128 FFMA per lane and held-out row) against warp-level tensor-core
+//      SYRK blocks of 8 held-out rows (8 x mma.sync.m16n8k8 TF32, single pass and 3-pass split) and of 16 rows in BF16
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cstdio>
@@ -160,6 +163,120 @@ __global__ void __launch_bounds__(512, 1) tmem_kernel(int iters, int warps_activ
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
+
+// ---- 4. Gram correction: FFMA rank-1 updates vs mma.sync SYRK ------------------------------------------------------
+// Work unit = one held-out row of one column (k^2 = 1024 multiply-adds). Rows are staged in shared memory the way the
+// solver's cp.async ring leaves them ([entry][KP] floats, padded to 40 floats per entry for the fragment reads).
+// MODE 0: FP32 FFMA, 8 lanes per column (4 columns per warp), lane owns 4 rows of the 32 x 32 matrix
+// MODE 1: TF32 mma.sync m16n8k8, one column per warp, 8 entries per block, single pass (8 LDS + 8 CVT + 8 MMA)
+// MODE 2: 3xTF32 (hi*hi + hi*lo + lo*hi): 24 MMA per block
+// MODE 3: BF16 mma.sync m16n8k16, 16 entries per block, single pass
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) gramcorr_kernel(int iters, int warps_active, unsigned long long* out_clk, float* sink) {
+    __shared__ __align__(16) float stage[16][16 * 40];  // per warp: 16 entries x 40 floats
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = lane; i < 16 * 40; i += 32) stage[warp][i] = 1.0f + (float)((i * 7 + warp) % 13) * 0.0625f;
+    __syncwarp();
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    float acc2[96];
+    if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 96; ++i) acc2[i] = 0.f;
+    }
+    const int g = lane >> 2, t = lane & 3;
+    unsigned long long t0 = clock64();
+    if (warp < warps_active) {
+        for (int it = 0; it < iters; ++it) {
+            if (MODE == 0) {
+                // 4 columns per warp, 8 lanes each: per held-out row 8 broadcast LDS.128 + 1 own LDS.128 + 128 FFMA
+                const int gi = lane >> 3, lig = lane & 7;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float4* st4 = reinterpret_cast<const float4*>(&stage[warp][(e * 4 + gi) * 40]);
+                    float f[32];
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        const float4 v = st4[i4];
+                        f[4 * i4] = v.x; f[4 * i4 + 1] = v.y; f[4 * i4 + 2] = v.z; f[4 * i4 + 3] = v.w;
+                    }
+                    const float4 mine = st4[lig];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        acc[i] = fmaf(mine.x, f[i], acc[i]);
+                        acc2[i] = fmaf(mine.y, f[i], acc2[i]);
+                        acc2[32 + i] = fmaf(mine.z, f[i], acc2[32 + i]);
+                        acc2[64 + i] = fmaf(mine.w, f[i], acc2[64 + i]);
+                    }
+                }
+            } else if (MODE == 1 || MODE == 2) {
+                float v[4], u[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { v[q] = stage[warp][t * 40 + g + 8 * q]; u[q] = stage[warp][(t + 4) * 40 + g + 8 * q]; }
+                uint32_t vh[4], uh[4], vl[4], ul[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(vh[q]) : "f"(v[q]));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(uh[q]) : "f"(u[q]));
+                    if (MODE == 2) {
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(vl[q]) : "f"(v[q] - __uint_as_float(vh[q])));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul[q]) : "f"(u[q] - __uint_as_float(uh[q])));
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float* d = &acc[(p * 4 + q) * 4];
+                        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                                     : "r"(vh[2 * p]), "r"(vh[2 * p + 1]), "r"(uh[2 * p]), "r"(uh[2 * p + 1]), "r"(vh[q]), "r"(uh[q]));
+                        if (MODE == 2) {
+                            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                                         : "r"(vh[2 * p]), "r"(vh[2 * p + 1]), "r"(uh[2 * p]), "r"(uh[2 * p + 1]), "r"(vl[q]), "r"(ul[q]));
+                            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                                         : "r"(vl[2 * p]), "r"(vl[2 * p + 1]), "r"(ul[2 * p]), "r"(ul[2 * p + 1]), "r"(vh[q]), "r"(uh[q]));
+                        }
+                    }
+            } else {
+                // BF16 m16n8k16: A frag 4 regs (2 bf16 each), B frag 2 regs; 16 entries per block
+                uint32_t a[2][4], b[4][2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float x0 = stage[warp][(2 * t) * 40 + g + 8 * q], x1 = stage[warp][(2 * t + 1) * 40 + g + 8 * q];
+                    const float y0 = stage[warp][(2 * t + 8) * 40 + g + 8 * q], y1 = stage[warp][(2 * t + 9) * 40 + g + 8 * q];
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b[q][0]) : "f"(x1), "f"(x0));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b[q][1]) : "f"(y1), "f"(y0));
+                }
+#pragma unroll
+                for (int p = 0; p < 2; ++p) { a[p][0] = b[2 * p][0]; a[p][1] = b[2 * p + 1][0]; a[p][2] = b[2 * p][1]; a[p][3] = b[2 * p + 1][1]; }
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float* d = &acc[(p * 4 + q) * 4];
+                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                                     : "r"(a[p][0]), "r"(a[p][1]), "r"(a[p][2]), "r"(a[p][3]), "r"(b[q][0]), "r"(b[q][1]));
+                    }
+            }
+        }
+    }
+    unsigned long long t1 = clock64();
+    if (lane == 0) atomicMax(&out_clk[blockIdx.x], t1 - t0);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += acc[i];
+    if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 96; ++i) s += acc2[i];
+    }
+    if (s == 123.456f) sink[0] = s;
+}
+
 int main() {
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
@@ -213,6 +330,25 @@ int main() {
         char name[64];
         snprintf(name, sizeof(name), "tcgen05.ld.32x32b.x1 dynamic column, %2d warps", wa);
         report(name, (double)wa * iters * 8, 128);
+    }
+    // 4. Gram correction: clk per (column, held-out row) unit per SM
+    for (int wa : {4, 8, 16}) {
+        auto run = [&](auto kern, const char* nm, double units_per_iter) {
+            for (int rep = 0; rep < 2; ++rep) {
+                cudaMemset(d_clk, 0, sizeof(unsigned long long) * sms);
+                kern<<<sms, 512>>>(iters, wa, d_clk, d_sink);
+                cudaDeviceSynchronize();
+            }
+            cudaMemcpy(clk.data(), d_clk, sizeof(unsigned long long) * sms, cudaMemcpyDeviceToHost);
+            double mx = 0;
+            for (int i = 0; i < sms; ++i) mx = clk[i] > mx ? (double)clk[i] : mx;
+            printf("%-40s %2d warps %10.0f clk  %7.3f clk per column-row per SM  (%6.1f FMA/clk/SM)\n", nm, wa, mx,
+                   mx / (units_per_iter * wa * iters), 1024.0 * units_per_iter * wa * iters / mx);
+        };
+        run(gramcorr_kernel<0>, "Gram corr: FFMA, 8 lanes/column", 8.0);
+        run(gramcorr_kernel<1>, "Gram corr: mma.sync TF32 1-pass", 8.0);
+        run(gramcorr_kernel<2>, "Gram corr: mma.sync 3xTF32", 8.0);
+        run(gramcorr_kernel<3>, "Gram corr: mma.sync BF16 1-pass", 16.0);
     }
     float probe[4];
     CK(cudaMemcpy(probe, d_sink, 16, cudaMemcpyDeviceToHost));

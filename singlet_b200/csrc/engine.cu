@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "misc.cuh"
 #include "nnls.cuh"
+#include "gramcorr.cuh"
 #include "spmm.cuh"
 #include "spmm_h16.cuh"
 
@@ -116,6 +117,9 @@ struct sgl_handle {
     DevBuf<uint32_t> shadow_meta;
     int precision = SGL_PRECISION_MIXED16;
     DevBuf<double> part, scal, losses, gram_w;
+    // tensor-core Gram correction (gramcorr.cuh): BF16 hi / mid pairs of the gather factor, G_M of a column chunk
+    DevBuf<uint16_t> bf_pairs;
+    DevBuf<float> gm;
     DevBuf<int64_t> counts;
     DevBuf<unsigned long long> workctr, held;
     // factor buffers of the fit in flight and the FP64 staging of factor up/downloads: kept across calls so
@@ -932,6 +936,9 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
                     // (tried for the 125,000-column case of a rank on 8 GPUs, 1.1 rounds of the grid: a 128-register build with 4 CTAs
                     //  or 16 one-warp CTAs per SM so that ONE round suffices, three columns per lane, and a sweep that skips warp-empty
                     //  slots. None beat 0.83 ms: the 128-register code is ~45 % slower per column -- profiles/r2_nnls.md)
+                    // (two CTAs per SM, i.e. two balanced rounds of 8 warps instead of 1.1 rounds of 12: 1.06 vs 1.05 ms of solver
+                    //  per iteration on that shard, and slower on the 250,000- and 500,000-column shards; handing the last 0.1
+                    //  round to the sub-warp kernel would cost 0.17 ms for 11,400 columns against the 0.33 ms it replaces)
                     if (false) {}
                     else if (ncol >= (int64_t)h->sm_count * 128 * 2) NNLS_LAUNCH(32, 128, 2)
                     else NNLS_LAUNCH(32, 32, 1)
@@ -958,7 +965,45 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
         }
         LAUNCH_CHECK(h);
     } else {
-        if (KPV <= 32) {
+        const char* gc_env = getenv("SGL_GRAMCORR");  // "ffma": keep the FP32 correction inside the solver (A/B tests)
+        if ((KPV == 16 || KPV == 32) && !(gc_env && gc_env[0] == 'f')) {
+            // Gram corrections on the tensor cores (gramcorr.cuh), a column chunk at a time (KP^2 floats per column), then
+            // the sub-warp solver with the corrections read back instead of accumulated (mptr = nullptr)
+            const int64_t rows_f = mask->X->nrow;  // rows of the gather factor
+            const int64_t nel = rows_f * KPV;
+            SGL_TRY(h->bf_pairs.ensure((size_t)nel * 2));
+            int64_t g = (nel / 4 + 255) / 256;
+            if (g > 8 * h->sm_count) g = 8 * h->sm_count;
+            if (KPV == 16) bf16_split_kernel<16><<<(unsigned)(g > 0 ? g : 1), 256, 0, h->stream>>>(F_in, nel, h->bf_pairs.p);
+            else bf16_split_kernel<32><<<(unsigned)(g > 0 ? g : 1), 256, 0, h->stream>>>(F_in, nel, h->bf_pairs.p);
+            LAUNCH_CHECK(h);
+            const int G = (KPV == 16) ? MaskedSubCfg<16>::G : MaskedSubCfg<32>::G;
+            const int64_t cols_per_cta = 4 * (int64_t)G;
+            const char* mb_env = getenv("SGL_GRAMCORR_MB");  // chunk budget (tests force several chunks)
+            const int64_t budget = (mb_env ? atoll(mb_env) : 1024) << 20;
+            int64_t chunk = budget / ((int64_t)KPV * KPV * 4) / cols_per_cta * cols_per_cta;
+            if (chunk < cols_per_cta) chunk = cols_per_cta;
+            const int64_t ncol_up = (ncol + cols_per_cta - 1) / cols_per_cta * cols_per_cta;
+            if (chunk > ncol_up) chunk = ncol_up;
+            SGL_TRY(h->gm.ensure((size_t)chunk * KPV * KPV));
+            n_parts = ncol_up / cols_per_cta;
+            SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
+            for (int64_t c0 = 0; c0 < ncol; c0 += chunk) {
+                const int64_t nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
+                const unsigned cg_grid = (unsigned)((nc + 3) / 4), sv_grid = (unsigned)((nc + cols_per_cta - 1) / cols_per_cta);
+                const int64_t blk0 = c0 / cols_per_cta;
+                if (KPV == 16) {
+                    gram_corr_mma_kernel<16><<<cg_grid, 128, 0, h->stream>>>(h->bf_pairs.p, colptr, mask->mptr, mask->mrec, c0, nc, h->gm.p);
+                    nnls_masked_sub_kernel<16, 1><<<sv_grid, 128, 0, h->stream>>>(Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, nullptr,
+                                                                                 nullptr, ncol, k, (float)L1, (float)L2, h->part.p, h->gm.p, blk0);
+                } else {
+                    gram_corr_mma_kernel<32><<<cg_grid, 128, 0, h->stream>>>(h->bf_pairs.p, colptr, mask->mptr, mask->mrec, c0, nc, h->gm.p);
+                    nnls_masked_sub_kernel<32, 1><<<sv_grid, 128, 0, h->stream>>>(Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, nullptr,
+                                                                                 nullptr, ncol, k, (float)L1, (float)L2, h->part.p, h->gm.p, blk0);
+                }
+                LAUNCH_CHECK(h);
+            }
+        } else if (KPV <= 32) {
             // sub-warp solver: G columns per warp; the whole CTA shares one column group (WS = 4) when the
             // one-group-per-warp grid would leave most SMs without work
             int G = 1;

@@ -460,7 +460,11 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
                        const float* __restrict__ F,        // gather factor [rows][KP]
                        const int64_t* __restrict__ colptr, const int64_t* __restrict__ mptr,
                        const uint2* __restrict__ mrec, int64_t ncol, int k, float L1, float L2,
-                       double* __restrict__ rowsum_part) {
+                       double* __restrict__ rowsum_part,
+                       // corrections computed beforehand on the tensor cores (gramcorr.cuh): gm[(col - first column of
+                       // this launch) * KP * KP + i * KP + j], with mptr == nullptr; blk0 = first CTA index of this launch
+                       // (a launch covers a column chunk: blk0 * columns-per-CTA is its first column)
+                       const float* __restrict__ gm = nullptr, int64_t blk0 = 0) {
     using C = MaskedSubCfg<KP>;
     constexpr int L = C::L, RPT = C::RPT, G = C::G;
     constexpr int WARPS = (WS == 2) ? 2 : C::WARPS;  // WS = 1: four column groups per CTA; WS = 2 / 4: the CTA shares one
@@ -476,7 +480,8 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
     const int lig = lane % L;  // lane inside its column's group: owns rows lig*RPT .. lig*RPT+RPT-1
     const int gi = lane / L;   // column slot inside the warp
     const int cgi = warp / WS, wsub = warp % WS;
-    const int64_t col = ((int64_t)blockIdx.x * CG + cgi) * G + gi;
+    const int64_t blk = (int64_t)blockIdx.x + blk0;
+    const int64_t col = (blk * CG + cgi) * G + gi;
     const bool in_range = col < ncol;
     const bool solve = in_range && (colptr[col] != colptr[col + 1]);
 
@@ -586,6 +591,17 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
             }
             __syncthreads();
         }
+    }
+
+    if (gm != nullptr && solve) {  // G_M from gram_corr_mma_kernel: my RPT rows of it
+        const float* src = gm + ((col - blk0 * (CG * G)) * KP + lig * RPT) * (int64_t)KP;
+#pragma unroll
+        for (int c = 0; c < RPT; ++c)
+#pragma unroll
+            for (int i4 = 0; i4 < KP / 4; ++i4) {
+                const float4 v = *reinterpret_cast<const float4*>(src + c * KP + 4 * i4);
+                a[c][4 * i4 + 0] = v.x; a[c][4 * i4 + 1] = v.y; a[c][4 * i4 + 2] = v.z; a[c][4 * i4 + 3] = v.w;
+            }
     }
 
     // ---- right-hand side, warm start, a_i = G - G_M (the 1e-15 jitters cancel, App. A-11) ----
@@ -746,7 +762,7 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) s += sred[w][t];
-        rowsum_part[(int64_t)blockIdx.x * KP + t] = s;
+        rowsum_part[blk * KP + t] = s;
     }
 }
 

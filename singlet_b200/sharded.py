@@ -414,7 +414,8 @@ def distributed_cross_validate_nmf(A, ranks, n_replicates=3, tol=1e-4, maxit=100
     processes of ``group`` (one process per GPU): the fits are independent, so every process uploads A, runs its share
     with ``sgl_ard_nmf_batch`` and the traces are gathered -- no data-path collective ("replicas" of the CV path, SURVEY.md
     8e). Every process returns the same DataFrame, identical to ``api.cross_validate_nmf`` on one GPU. ``seed``: R's
-    ``set.seed`` value (all processes must draw the same w_init and mask seeds)."""
+    ``set.seed`` value (all processes must draw the same w_init and mask seeds); ``None`` continues the global stream of
+    ``api.set_seed`` like ``api.cross_validate_nmf`` does."""
     import pandas as pd
 
     from . import api
@@ -422,8 +423,13 @@ def distributed_cross_validate_nmf(A, ranks, n_replicates=3, tol=1e-4, maxit=100
 
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    r = RRng(0)
-    r.set_seed(123 if seed is None else seed)
+    # seed = None: the global R-style stream, exactly like api.cross_validate_nmf (every process must have called
+    # api.set_seed with the same value); an explicit seed draws from a private stream and leaves the global one alone
+    if seed is None:
+        r = api._RNG
+    else:
+        r = RRng(0)
+        r.set_seed(seed)
     ranks = [int(k) for k in np.atleast_1d(ranks)]
     A = api._as_csc(A)
     m = A.shape[0]

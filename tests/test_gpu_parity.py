@@ -240,6 +240,41 @@ def test_ard_nmf_matches_oracle(handle, oracle, k, maxit, trace):
     assert abs(tr_dev - tr_ref) <= MSE_RTOL * tr_ref
 
 
+@pytest.mark.parametrize("k", [12, 16, 20, 32])
+def test_tensor_core_gram_correction_matches_fp32_and_oracle(handle, oracle, monkeypatch, k):
+    """The masked solver's per-column correction a_i = a - W_M W_M^T (src/singlet.cpp:460-462) on the tensor cores (gramcorr.cuh:
+    two BF16-split mma passes, the default for padded ranks 16 / 32) against the FP32 FFMA accumulation inside the solver
+    (SGL_GRAMCORR=ffma) and against the FP64 oracle; cutting the columns into many chunks (SGL_GRAMCORR_MB=0: one CTA's
+    columns per chunk) must not change a bit."""
+    from singlet_b200 import api, synth
+
+    m, n = 900, 650
+    A, At = _mk(m, n, 0.1, seed=70 + k, empty_cols=(3, 640))
+    w0 = synth.w_init(k, m, seed=k + 5)
+    args = (A, At, 0.0, 6, False, 0.01, 0.0, 0, w0, 77, 12, 10.0, 2)
+    monkeypatch.delenv("SGL_GRAMCORR", raising=False)
+    monkeypatch.delenv("SGL_GRAMCORR_MB", raising=False)
+    mma = api.c_ard_nmf(*args)
+    monkeypatch.setenv("SGL_GRAMCORR_MB", "0")
+    chunked = api.c_ard_nmf(*args)
+    monkeypatch.delenv("SGL_GRAMCORR_MB")
+    monkeypatch.setenv("SGL_GRAMCORR", "ffma")
+    ffma = api.c_ard_nmf(*args)
+    monkeypatch.delenv("SGL_GRAMCORR")
+    for key in ("w", "d", "h", "test_mse"):
+        assert np.array_equal(mma[key], chunked[key]), key
+    ref = oracle.ard_nmf(A, At, w0, 77, 12, tol=0.0, maxit=6, L1=0.01, L2=0.0, overfit_threshold=10.0, trace_test_mse=2)
+    for dev in (mma, ffma):
+        assert list(dev["iter"]) == list(ref["iter"])
+        assert np.allclose(dev["test_mse"], ref["test_mse"], rtol=MSE_RTOL)
+        perm = match_factors(ref["w"], dev["w"])
+        assert min_factor_cor(ref["w"], dev["w"], perm) >= COR_MIN and min_factor_cor(ref["h"], dev["h"], perm) >= COR_MIN
+    # the two device paths agree far more closely with each other than either needs to with the FP64 reference
+    assert np.allclose(mma["test_mse"], ffma["test_mse"], rtol=2e-5)
+    assert np.allclose(mma["d"], ffma["d"], rtol=1e-3)
+    assert not np.array_equal(mma["w"], ffma["w"])  # and they ARE different code paths
+
+
 def test_ard_overfit_break(handle, oracle):
     """The early `break` on score_overfit > threshold leaves iter_ un-incremented (App. A-13)."""
     from singlet_b200 import api, synth
