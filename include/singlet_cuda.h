@@ -253,7 +253,8 @@ int sgl_dev_update_masked(sgl_handle* h, const sgl_matrix* X, const sgl_mask* ma
                           int k, const double* gram, double L1, double L2, double* rowsum);
 /* mse_test (src/singlet.cpp:536-568) over the cell columns of `mask` (mask_t = 0): writes the SUM of
  * per-column losses to loss_sum[0] (double, device); divide by the global n afterwards.
- * which = 0: held-out entries (test); 1: the entries that are not held out (train, harness-defined). */
+ * which = 0: held-out entries (test); 1: the entries that are not held out (train, harness-defined); 2: both in ONE pass
+ * over the held-out lists and the non-zeros (the fused train/test loss kernel): loss_sum[0] = test, loss_sum[1] = train. */
 int sgl_dev_mse(sgl_handle* h, const sgl_matrix* A, const sgl_mask* mask, const float* W, const double* d,
                 const float* H, int k, int which, double* loss_sum);
 

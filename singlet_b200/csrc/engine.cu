@@ -1214,18 +1214,22 @@ static int dev_mse(sgl_handle* h, const sgl_matrix* A, const sgl_mask* mask, con
     if (which == 0 && !mask) return fail(SGL_EINVAL, "test MSE needs a mask");
     if (mask && mask->mask_t != 0) return fail(SGL_EINVAL, "MSE needs the cell-column mask (mask_t = 0)");
     if (A->ncol == 0) {
-        SGL_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), h->stream));
+        SGL_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double) * (which == 2 ? 2 : 1), h->stream));
         return SGL_OK;
     }
-    SGL_TRY(h->losses.ensure((size_t)A->ncol));
+    if (which == 2 && !mask) return fail(SGL_EINVAL, "the fused test + train MSE needs a mask");
+    if (which < 0 || which > 2) return fail(SGL_EINVAL, "which must be 0 (test), 1 (train) or 2 (both, one pass)");
+    SGL_TRY(h->losses.ensure((size_t)A->ncol * (which == 2 ? 2 : 1)));
     SGL_TRY(h->gram_w.ensure((size_t)KPV * KPV));
-    if (which == 1) SGL_TRY(dev_gram(h, W, k, A->nrow, h->gram_w.p, false));
+    if (which >= 1) SGL_TRY(dev_gram(h, W, k, A->nrow, h->gram_w.p, false));
     const unsigned grid = blocks_for(A->ncol, 4);
     DISPATCH_KP(KPV, (mse_kernel<KP><<<grid, 128, 0, h->stream>>>(A->colptr, A->rec, mask ? mask->mptr : nullptr,
                                                                   mask ? mask->mrec : nullptr, W, d, H, h->gram_w.p, A->nrow,
-                                                                  A->ncol, k, which, h->losses.p)));
+                                                                  A->ncol, k, which, h->losses.p, h->losses.p + A->ncol)));
     LAUNCH_CHECK(h);
-    return reduce_partials(h, h->losses.p, A->ncol, 1, loss_sum);
+    SGL_TRY(reduce_partials(h, h->losses.p, A->ncol, 1, loss_sum));
+    if (which == 2) SGL_TRY(reduce_partials(h, h->losses.p + A->ncol, A->ncol, 1, loss_sum + 1));
+    return SGL_OK;
 }
 
 static int factor_upload(sgl_handle* h, const double* host, int k, int64_t cols, float* dev) {

@@ -404,10 +404,15 @@ mask_records_kernel(MaskGen gen, int64_t ncol, const int64_t* __restrict__ colpt
 }
 
 // ----------------------------------------------------------------------------------------------
-// mse_test (src/singlet.cpp:536-568) / harness train MSE, warp per cell column.
+// mse_test (src/singlet.cpp:536-568) / harness train MSE, warp per cell column -- the fused loss kernel.
 //   test : mean over held-out genes g of (sum_f W[g][f] d[f] H[c][f] - A[g][c])^2   (0 if none)
 //   train: the same over the genes that are NOT held out (all m genes when mask == NULL), via
 //          S_all - S_heldout with S_all = hd^T (W^T W) hd - 2 sum_nz a*pred + sum_nz a^2.
+// which = 0: test, 1: train, 2: both from one pass over the held-out list and the non-zeros.
+// LPE = KP / 4 lanes cooperate on one entry: each reads 16 bytes of the gene's W row, so a group reads one contiguous
+// 4 * KP-byte piece (a whole 128-byte line at KP = 32) and the warp covers 32 / LPE entries per step; the partial dot
+// products are folded with log2(LPE) shuffles. (One entry per lane -- every lane walking a whole row of its own -- kept the
+// L1 at 98 % of its wavefront rate: 2.17 ms for 7.5e7 held-out entries at k = 32, profiles/r2_masked.md.)
 // Writes per-column losses; the caller reduces them in fixed order.
 // ----------------------------------------------------------------------------------------------
 template <int KP>
@@ -415,24 +420,26 @@ __global__ void __launch_bounds__(128)
 mse_kernel(const int64_t* __restrict__ colptr, const uint2* __restrict__ rec, const int64_t* __restrict__ mptr,
            const uint2* __restrict__ mrec, const float* __restrict__ W, const double* __restrict__ d,
            const float* __restrict__ H, const double* __restrict__ gram_w /*[KP*KP] W^T W, jitter irrelevant*/,
-           int64_t m_genes, int64_t ncol, int k, int which, double* __restrict__ losses) {
+           int64_t m_genes, int64_t ncol, int k, int which, double* __restrict__ losses,
+           double* __restrict__ losses_train /* which == 2: test loss -> losses, train loss -> losses_train, one pass */) {
+    constexpr int LPE = KP / 4, EPS = 32 / LPE;  // lanes per entry, entries per warp step
     const int lane = threadIdx.x & 31;
+    const int lig = lane % LPE, grp = lane / LPE;
     const int64_t col = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (col >= ncol) return;
-    // hd[f] = d[f] * h[c][f], kept by every lane
-    float hd[KP];
+    if (col >= ncol) return;  // warp-uniform
+    // my four entries of hd[f] = d[f] * h[c][f]
+    float hd[4];
 #pragma unroll
-    for (int f = 0; f < KP; ++f) hd[f] = (f < k) ? (float)(d[f] * (double)H[col * KP + f]) : 0.f;
-
-    auto predict = [&](int64_t gene) {
-        const float4* wr = reinterpret_cast<const float4*>(W + gene * KP);
-        float p = 0.f;
+    for (int q = 0; q < 4; ++q) {
+        const int f = 4 * lig + q;
+        hd[q] = (f < k) ? (float)(d[f] * (double)H[col * KP + f]) : 0.f;
+    }
+    auto predict = [&](int64_t gene) {  // all lanes of the warp call it together; the result is on every lane of the group
+        const float4 w4 = *reinterpret_cast<const float4*>(W + gene * KP + 4 * lig);
+        float p = w4.x * hd[0];
+        p = fmaf(w4.y, hd[1], p); p = fmaf(w4.z, hd[2], p); p = fmaf(w4.w, hd[3], p);
 #pragma unroll
-        for (int f4 = 0; f4 < KP / 4; ++f4) {
-            const float4 w4 = wr[f4];
-            p = fmaf(w4.x, hd[4 * f4 + 0], p); p = fmaf(w4.y, hd[4 * f4 + 1], p);
-            p = fmaf(w4.z, hd[4 * f4 + 2], p); p = fmaf(w4.w, hd[4 * f4 + 3], p);
-        }
+        for (int o = 1; o < LPE; o <<= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
         return p;
     };
 
@@ -441,34 +448,37 @@ mse_kernel(const int64_t* __restrict__ colptr, const uint2* __restrict__ rec, co
     if (mptr != nullptr) {
         const int64_t mb = mptr[col], me = mptr[col + 1];
         n_held = me - mb;
-        for (int64_t p = mb + lane; p < me; p += 32) {
-            const uint2 r = mrec[p];
+        for (int64_t base = mb; base < me; base += EPS) {  // warp-uniform trip count
+            const int64_t p = base + grp;
+            const bool ok = p < me;
+            const uint2 r = ok ? mrec[p] : make_uint2(0u, 0u);
             const double res = (double)predict((int64_t)r.x) - (double)__uint_as_float(r.y);
-            s_held += res * res;
+            if (ok && lig == 0) s_held += res * res;
         }
         s_held = warp_sum(s_held);
     }
-    if (which == 0) {
-        if (lane == 0) losses[col] = n_held > 0 ? s_held / (double)n_held : 0.0;
-        return;
-    }
+    if (which != 1 && lane == 0) losses[col] = n_held > 0 ? s_held / (double)n_held : 0.0;
+    if (which == 0) return;
     // train: S_all
     double quad = 0.0;
     for (int i = lane; i < k; i += 32) {
         double row = 0.0;
-        for (int j = 0; j < k; ++j)  // re-derive hd[j] from memory: keeps hd[] statically indexed (registers)
-            row += gram_w[i * KP + j] * (double)(float)(d[j] * (double)H[col * KP + j]);
+        for (int j = 0; j < k; ++j) row += gram_w[i * KP + j] * (double)(float)(d[j] * (double)H[col * KP + j]);
         quad += row * (double)(float)(d[i] * (double)H[col * KP + i]);
     }
     double lin = 0.0;
-    for (int64_t p = colptr[col] + lane; p < colptr[col + 1]; p += 32) {
-        const uint2 r = rec[p];
+    const int64_t cb = colptr[col], ce = colptr[col + 1];
+    for (int64_t base = cb; base < ce; base += EPS) {
+        const int64_t p = base + grp;
+        const bool ok = p < ce;
+        const uint2 r = ok ? rec[p] : make_uint2(0u, 0u);
         const double a = (double)__uint_as_float(r.y);
-        lin += a * a - 2.0 * a * (double)predict((int64_t)r.x);
+        const double pr = (double)predict((int64_t)r.x);
+        if (ok && lig == 0) lin += a * a - 2.0 * a * pr;
     }
     const double s_all = warp_sum(quad + lin);
     const int64_t n_train = m_genes - n_held;
-    if (lane == 0) losses[col] = n_train > 0 ? (s_all - s_held) / (double)n_train : 0.0;
+    if (lane == 0) (which == 2 ? losses_train : losses)[col] = n_train > 0 ? (s_all - s_held) / (double)n_train : 0.0;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -568,6 +568,12 @@ def test_device_train_and_test_mse(oracle):
         be.mse(hA, mask, W, dd, H, k, 1, out)
         ref = oracle.mse_train(A, w, d, h, 123, 20)
         assert abs(float(out[0]) / n - ref) <= 1e-5 * ref
+        t_test, t_train = float(out[0]), None
+        be.mse(hA, mask, W, dd, H, k, 0, out)
+        t_test, t_train = float(out[0]), t_test
+        both = be.zeros_f64(2)
+        be.mse(hA, mask, W, dd, H, k, 2, both)  # which = 2: both losses from ONE pass, bit-identical to the separate passes
+        assert float(both[0]) == t_test and float(both[1]) == t_train
         be.mse(hA, None, W, dd, H, k, 1, out)  # no mask: all m entries of every column
         ref = oracle.mse_train(A, w, d, h)
         assert abs(float(out[0]) / n - ref) <= 1e-5 * ref
