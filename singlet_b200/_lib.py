@@ -137,6 +137,21 @@ SYMBOLS = [
 ]
 
 
+def _point_at_bundled_nccl():
+    """The multi-GPU entry points bind NCCL at run time (csrc/multi.cu). In a Python process that also imports torch, both
+    must use the SAME libnccl.so.2 (the loader keys it by soname): point the library at the copy bundled with torch
+    (site-packages/nvidia/nccl/lib) unless the caller chose one with SGL_NCCL_LIB. Never imports torch."""
+    if os.environ.get("SGL_NCCL_LIB"):
+        return
+    import sys
+
+    for base in sys.path:
+        cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if base and os.path.exists(cand):
+            os.environ["SGL_NCCL_LIB"] = cand
+            return
+
+
 def load():
     """Load the shared library (once) and bind every declared symbol. Raises if it is missing."""
     global _lib
@@ -145,6 +160,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise SingletCudaError(SGL_ENODEVICE, f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback)")
+    _point_at_bundled_nccl()
     lib = C.CDLL(LIB_PATH)
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree

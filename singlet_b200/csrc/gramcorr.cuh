@@ -6,7 +6,7 @@
 //
 // One warp = one column. The operand is the OTHER factor F (k x rows, FP32). It is split once per half-iteration into two
 // BF16 planes, hi = bf16(F) and mid = bf16(F - hi): 16 mantissa bits together. The held-out rows are gathered 16 at a time
-// into a shared-memory ring with cp.async (64 + 64 bytes per row at KP = 32, the same bytes as the FP32 row), read as
+// into a shared-memory ring with cp.async (64 + 64 contiguous bytes per row at KP = 32, the same bytes as the FP32 row), read as
 // mma fragments with ldmatrix.trans (the A operand hi^T and the B operand hi / mid are the SAME registers: A[i][e] =
 // F[e][i] = B[e][i]) and accumulated in FP32 by mma.sync.m16n8k16 (SASS HMMA.16816.F32.BF16):
 //     D1 += hi^T hi,   D2 += hi^T mid,    G_M = D1 + D2 + D2^T            (mid^T mid ~ 2^-18 |G_M| is dropped)
@@ -53,15 +53,21 @@ template <int KP>
 struct GramCorrCfg {
     static_assert(KP == 16 || KP == 32, "tensor-core Gram correction: padded ranks 16 and 32");
     static constexpr int MT = KP / 16, NT = KP / 8;     // 16-row and 8-column tiles of the KP x KP output
-    static constexpr int ROW_BYTES = KP * 2;            // one plane of one gathered row
-    static constexpr int STRIDE = ROW_BYTES + 16;       // 80 / 48 bytes: the 8 row addresses of an ldmatrix tile hit 8 distinct 16-byte bank groups
+    static constexpr int EB = KP * 4;                   // bytes of one gathered entry: hi row | mid row, as it lies in global memory
+    static constexpr int CPE = EB / 16;                 // 16-byte chunks per entry (8 / 4)
+    static constexpr int EPL = 128 / EB;                // entries per 128-byte line of the ring (1 / 2)
+    static constexpr int SW_MASK = CPE - 1;             // chunk c of entry e sits at chunk ((e % EPL) * CPE + c) ^ ((e / EPL) & SW_MASK) of
+                                                        // line e / EPL: unpadded lines, so the 8 lanes that copy one line with cp.async write
+                                                        // one conflict-free wavefront, AND the 8 row addresses of an ldmatrix tile (8
+                                                        // consecutive entries, same logical chunk) fall into 8 distinct 16-byte bank groups
     static constexpr int BLK = 16;                      // held-out rows per block = K of one mma
-    static constexpr int PLANE_BYTES = BLK * STRIDE;
-    static constexpr int STAGE_BYTES = 2 * PLANE_BYTES;
+    static constexpr int STAGE_BYTES = BLK * EB;
     static constexpr int STAGES = 4;
     static constexpr int WARPS = 4;
-    static constexpr int CHUNKS = ROW_BYTES / 16;       // 16-byte cp.async chunks per plane row
     static constexpr int WARP_BYTES = STAGES * STAGE_BYTES;
+    __host__ __device__ static constexpr uint32_t offset(int e, int c) {  // byte offset of chunk c of entry e inside a stage
+        return (uint32_t)((e / EPL) * 128 + ((((e % EPL) * CPE + c) ^ ((e / EPL) & SW_MASK)) * 16));
+    }
     static_assert(WARP_BYTES >= KP * (KP + 1) * 4, "the transpose scratch reuses the ring");
 };
 
@@ -103,24 +109,25 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
             for (int c = 0; c < 4; ++c) { d1[p][q][c] = 0.f; d2[p][q][c] = 0.f; }
 
     // A block is 16 entries of 4 * KP contiguous bytes (hi row | mid row). One cp.async instruction copies 32 / CPE whole
-    // entries, CPE = KP / 4 adjacent lanes covering the 4 * KP bytes of one entry in order, so that every request of the
-    // instruction is made of whole 32-byte sectors (one lane per 16 bytes with the two planes 2 * KP bytes apart, as first
-    // written, fetched every sector twice: 264 B per entry over the L2 crossbar instead of 128 -- profiles/r2_masked.md).
-    // The row index of entry e of the block is held by lane e.
-    constexpr int CPE = KP / 4, EPI = 32 / CPE, NI = C::BLK / EPI;
+    // entries, CPE adjacent lanes covering the bytes of one entry in order, so that every request of the instruction is made
+    // of whole 32-byte sectors and lands in shared memory as whole conflict-free lines. (One lane per 16 bytes with the two
+    // planes 2 * KP bytes apart, as first written, fetched every sector twice: 264 B per entry over the L2 crossbar; a padded
+    // 144-byte row split the shared-memory side of each request into ~10 wavefronts and still moved 200 B per entry --
+    // profiles/r2_masked.md.) The row index of entry e of the block is held by lane e.
+    constexpr int CPE = C::CPE, EPI = 32 / CPE, NI = C::BLK / EPI;
     auto load_idx = [&](int blk) -> uint32_t {
         const int t = blk * C::BLK + (lane & 15);
         return (t < n) ? mrec[mb + t].x : 0u;
     };
     auto issue = [&](int blk, int stage, uint32_t idxreg) {
-        const int chunk = lane % CPE, plane = chunk / (CPE / 2), pc = chunk % (CPE / 2);
+        const int chunk = lane % CPE;
 #pragma unroll
         for (int q = 0; q < NI; ++q) {
             const int e = q * EPI + lane / CPE;
             const uint32_t row = __shfl_sync(0xffffffffu, idxreg, e);
             const bool ok = blk * C::BLK + e < n;  // entries past the end are zero-filled: they add nothing
             const uint16_t* src = pairs + (int64_t)row * (2 * KP) + chunk * 8;
-            const uint32_t dst = ring + (uint32_t)(stage * C::STAGE_BYTES + plane * C::PLANE_BYTES + e * C::STRIDE + pc * 16);
+            const uint32_t dst = ring + (uint32_t)(stage * C::STAGE_BYTES) + C::offset(e, chunk);
             cp_async16(dst, src, ok ? 16u : 0u);
         }
     };
@@ -129,31 +136,50 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
         issue(s, s, load_idx(s));
         cp_async_commit();
     }
-    uint32_t idx_pref = load_idx(C::STAGES);
-    // ldmatrix row address of this lane: tile ti = lane / 8 of an x4 load is (entry half h = ti & 1, factor octet 2 j + (ti >> 1))
-    const uint32_t lm_off = (uint32_t)((8 * ((lane >> 3) & 1) + (lane & 7)) * C::STRIDE + (lane >> 4) * 16);
-    for (int b = 0; b < nblk; ++b) {
+    // Row indices (streamed from HBM: 8 bytes per held-out entry, not L2-resident like the factor) are fetched two blocks
+    // before the copy that needs them is issued. The loop is unrolled by U = 2 with one index register per residue: rotating
+    // two registers made the compiler wait for the younger load at the rotation itself (55 % of the stall samples), one
+    // block of distance left 17 % of the samples on the shuffle that consumes the index, two blocks 25 % of fewer samples
+    // (1.15 -> 1.05 ms), and four blocks (U = 4) was slower again (profiles/r2_masked.md).
+    constexpr int U = 2;
+    static_assert(C::STAGES % U == 0, "block b and block b + STAGES share an index register");
+    uint32_t idx_r[U];
+#pragma unroll
+    for (int r = 0; r < U; ++r) idx_r[r] = load_idx(C::STAGES + r);
+    // Two fragment orders of the same tiles: for the B operand an x4 load returns {P[2j], Q[2j], P[2j+1], Q[2j+1]} (tile ti:
+    // entry half h = ti & 1, factor octet 2 j + (ti >> 1)) -- the register PAIRS mma wants; for the A operand {P[2j], P[2j+1],
+    // Q[2j], Q[2j+1]} (h = ti >> 1, octet 2 j + (ti & 1)) -- the register QUAD of m-tile j. The hi plane is loaded in both
+    // orders: two more LDSM per block instead of four register moves in front of every HMMA.
+    const int lm_e = 8 * ((lane >> 3) & 1) + (lane & 7), lm_q = lane >> 4;
+    const int la_e = 8 * (lane >> 4) + (lane & 7), la_q = (lane >> 3) & 1;
+    auto block = [&](int b, uint32_t& idx_mine) {
         cp_async_wait<C::STAGES - 1>();
         __syncwarp();
         const uint32_t st = ring + (uint32_t)((b % C::STAGES) * C::STAGE_BYTES);
         // P[q] = {F[2t][8q+g], F[2t+1][8q+g]}, Q[q] = the same for entries 8 + 2t, 9 + 2t  (g = lane / 4, t = lane % 4)
-        uint32_t Ph[NT], Qh[NT], Pm[NT], Qm[NT];
+        uint32_t Ah[MT][4], Bh[NT / 2][4], Bm[NT / 2][4];
 #pragma unroll
         for (int j = 0; j < NT / 2; ++j) {
-            ldmatrix_x4_trans(st + lm_off + 32u * j, Ph[2 * j], Qh[2 * j], Ph[2 * j + 1], Qh[2 * j + 1]);
-            ldmatrix_x4_trans(st + C::PLANE_BYTES + lm_off + 32u * j, Pm[2 * j], Qm[2 * j], Pm[2 * j + 1], Qm[2 * j + 1]);
+            ldmatrix_x4_trans(st + C::offset(la_e, 2 * j + la_q), Ah[j][0], Ah[j][1], Ah[j][2], Ah[j][3]);
+            ldmatrix_x4_trans(st + C::offset(lm_e, 2 * j + lm_q), Bh[j][0], Bh[j][1], Bh[j][2], Bh[j][3]);
+            ldmatrix_x4_trans(st + C::offset(lm_e, CPE / 2 + 2 * j + lm_q), Bm[j][0], Bm[j][1], Bm[j][2], Bm[j][3]);
         }
 #pragma unroll
         for (int p = 0; p < MT; ++p)
 #pragma unroll
             for (int q = 0; q < NT; ++q) {
-                mma_bf16_16816(d1[p][q], Ph[2 * p], Ph[2 * p + 1], Qh[2 * p], Qh[2 * p + 1], Ph[q], Qh[q]);
-                mma_bf16_16816(d2[p][q], Ph[2 * p], Ph[2 * p + 1], Qh[2 * p], Qh[2 * p + 1], Pm[q], Qm[q]);
+                mma_bf16_16816(d1[p][q], Ah[p][0], Ah[p][1], Ah[p][2], Ah[p][3], Bh[q / 2][2 * (q & 1)], Bh[q / 2][2 * (q & 1) + 1]);
+                mma_bf16_16816(d2[p][q], Ah[p][0], Ah[p][1], Ah[p][2], Ah[p][3], Bm[q / 2][2 * (q & 1)], Bm[q / 2][2 * (q & 1) + 1]);
             }
         __syncwarp();  // every lane has read the stage
-        issue(b + C::STAGES, b % C::STAGES, idx_pref);
+        issue(b + C::STAGES, b % C::STAGES, idx_mine);
         cp_async_commit();
-        idx_pref = load_idx(b + C::STAGES + 1);
+        idx_mine = load_idx(b + C::STAGES + U);
+    };
+    for (int b = 0; b < nblk; b += U) {
+#pragma unroll
+        for (int r = 0; r < U; ++r)
+            if (b + r < nblk) block(b + r, idx_r[r]);  // warp-uniform
     }
     cp_async_wait<0>();
     __syncwarp();

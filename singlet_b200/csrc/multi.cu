@@ -64,10 +64,17 @@ NcclApi* nccl_api() {
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
+        // Order: an explicit path (SGL_NCCL_LIB; the Python binding points it at the NCCL bundled with torch), a libnccl the
+        // process has already loaded, the system library. The loader keys libraries by soname, so whichever libnccl.so.2 comes
+        // first is the one a later `import torch` binds to as well: loading the system 2.27 before torch (built against its
+        // bundled 2.28) made torch fail with "undefined symbol: ncclDevCommCreate". RTLD_LOCAL: nothing is exported.
+        const char* env = getenv("SGL_NCCL_LIB");
+        if (env && env[0]) api.lib = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+        if (!api.lib) api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char* nm : names) {
-            api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
             if (api.lib) break;
+            api.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
         }
         if (!api.lib) {
             api.error = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found");
