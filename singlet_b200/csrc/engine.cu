@@ -939,6 +939,8 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
                     // (two CTAs per SM, i.e. two balanced rounds of 8 warps instead of 1.1 rounds of 12: 1.06 vs 1.05 ms of solver
                     //  per iteration on that shard, and slower on the 250,000- and 500,000-column shards; handing the last 0.1
                     //  round to the sub-warp kernel would cost 0.17 ms for 11,400 columns against the 0.33 ms it replaces)
+                    // (14 one-warp CTAs per SM -- __launch_bounds__(32, 14), which ptxas answers with a 128-register build -- so that
+                    //  125,000 columns make one round: 1.086 vs 1.068 ms, no gain either)
                     if (false) {}
                     else if (ncol >= (int64_t)h->sm_count * 128 * 2) NNLS_LAUNCH(32, 128, 2)
                     else NNLS_LAUNCH(32, 32, 1)
