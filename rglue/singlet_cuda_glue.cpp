@@ -7,7 +7,9 @@
 // byte for byte. Everything below only unpacks the R objects, calls the C ABI of libsinglet_cuda.so
 // (include/singlet_cuda.h) and wraps the results. R is not installed in the build container, so this
 // file is compiled where the package is built; the same calls are exercised
-// from Python (singlet_b200/api.py) in the test-suite.
+// from Python (singlet_b200/api.py) in the test-suite. Further down: the multi-GPU bodies of the two *_sparse_list entry
+// points (sgl_multi_*: one R process, all GPUs of the box) and the IVSparse functions of src/singlet.cpp:783-995
+// (save_IVSparse, read_IVSparse, run_nmf_on_sparsematrix_list) on top of sgl_ivsparse_*.
 #include <Rcpp.h>
 #include <RcppEigen.h>
 #include <singlet.h>  // Rcpp::SparseMatrix (inst/include/singlet.h:36-102)
@@ -259,4 +261,132 @@ Rcpp::List c_ard_nmf_batch(Rcpp::SparseMatrix& A, Rcpp::SparseMatrix& At, const 
                                     Rcpp::Named("score_overfit") = Rcpp::NumericVector(so[j].begin(), so[j].begin() + q));
     }
     return out;
+}
+
+// ---- several GPUs from the one R process ------------------------------------------------------------------
+// The chunk-list entry points are what shards: with options(singlet.gpus = G > 1) the two *_sparse_list functions above are
+// replaced by these bodies. `At_` is accepted and ignored (the transposed blocks are built on the devices), so the
+// "distributed transpose" of R/cross_validate_nmf.R:37-50 can be dropped by a maintainer but does no harm.
+namespace {
+sgl_multi* multi(int n_gpus) {  // one multi-GPU context per R session
+    static sgl_multi* mg = nullptr;
+    if (!mg && sgl_multi_create(n_gpus, nullptr, &mg) != SGL_OK) Rcpp::stop(sgl_last_error());
+    return mg;
+}
+}  // namespace
+
+Rcpp::List c_nmf_sparse_list_multi(int n_gpus, Rcpp::List A_, const double tol, const uint16_t maxit, const bool verbose,
+                                   const double L1, const double L2, Eigen::MatrixXd w) {
+    std::vector<Rcpp::SparseMatrix> A = as_list(A_);
+    std::vector<sgl_csc> a = views(A);
+    const int k = (int)w.rows();
+    int64_t n = 0;
+    for (auto& c : a) n += c.ncol;
+    Eigen::MatrixXd h(k, n);
+    Eigen::VectorXd d(k);
+    Progress p{verbose, false};
+    sgl_callbacks cb = callbacks(p);
+    if (verbose) Rprintf("\n%4s | %8s \n---------------\n", "iter", "tol");
+    check(sgl_multi_nmf(multi(n_gpus), a.data(), (int)a.size(), nullptr, 0, tol, maxit, L1, L1, L2, L2, k, w.data(), d.data(), h.data(),
+                        nullptr, nullptr, &cb));
+    return Rcpp::List::create(Rcpp::Named("w") = w, Rcpp::Named("d") = d, Rcpp::Named("h") = h);
+}
+
+Rcpp::List c_ard_nmf_sparse_list_multi(int n_gpus, Rcpp::List A_, const double tol, const uint16_t maxit, const bool verbose,
+                                       const double L1, const double L2, Eigen::MatrixXd w, const uint64_t rng_seed,
+                                       const uint64_t inv_density, const double overfit_threshold, const uint16_t trace_test_mse) {
+    std::vector<Rcpp::SparseMatrix> A = as_list(A_);
+    std::vector<sgl_csc> a = views(A);
+    const int k = (int)w.rows();
+    int64_t n = 0;
+    for (auto& c : a) n += c.ncol;
+    Eigen::MatrixXd h(k, n);
+    Eigen::VectorXd d(k);
+    const int cap = (int)maxit + 2;
+    std::vector<double> mse(cap), ft(cap), so(cap);
+    std::vector<int32_t> it(cap);
+    sgl_trace tr{mse.data(), it.data(), ft.data(), so.data(), cap, 0};
+    Progress p{verbose, true};
+    sgl_callbacks cb = callbacks(p);
+    check(sgl_multi_ard_nmf(multi(n_gpus), a.data(), (int)a.size(), nullptr, 0, tol, maxit, L1, L2, k, w.data(), d.data(), h.data(),
+                            rng_seed, inv_density, overfit_threshold, trace_test_mse, &tr, &cb));
+    return Rcpp::List::create(Rcpp::Named("w") = w, Rcpp::Named("d") = d, Rcpp::Named("h") = h,
+                              Rcpp::Named("test_mse") = Rcpp::NumericVector(mse.begin(), mse.begin() + tr.length),
+                              Rcpp::Named("iter") = Rcpp::IntegerVector(it.begin(), it.begin() + tr.length),
+                              Rcpp::Named("tol") = Rcpp::NumericVector(ft.begin(), ft.begin() + tr.length),
+                              Rcpp::Named("score_overfit") = Rcpp::NumericVector(so.begin(), so.begin() + tr.length));
+}
+
+// ---- IVSparse wire formats (reference src/singlet.cpp:783-995) -----------------------------------------
+// save_IVSparse / build_IVCSC2 / write_IVCSC / read_IVSparse keep their signatures and file names; the codec is the library's.
+namespace {
+std::vector<unsigned char> ivcsc_image(std::vector<sgl_csc>& a, int level) {
+    const int64_t n = sgl_ivsparse_encode(a.data(), (int)a.size(), level, nullptr, 0);
+    if (n < 0) Rcpp::stop(sgl_last_error());
+    std::vector<unsigned char> img((size_t)n);
+    if (sgl_ivsparse_encode(a.data(), (int)a.size(), level, img.data(), (uint64_t)img.size()) < 0) Rcpp::stop(sgl_last_error());
+    return img;
+}
+void write_file(const char* path, const std::vector<unsigned char>& img) {
+    FILE* fp = std::fopen(path, "wb");
+    if (!fp) Rcpp::stop("cannot open the output file");
+    std::fwrite(img.data(), 1, img.size(), fp);
+    std::fclose(fp);
+}
+}  // namespace
+
+//[[Rcpp::export]]
+bool save_IVSparse(Rcpp::List A_, bool verbose = true) {
+    std::vector<Rcpp::SparseMatrix> A = as_list(A_);
+    std::vector<sgl_csc> a = views(A);
+    if (verbose) Rprintf("writing to IVCSC_matrix.ivsparse\n");
+    write_file("IVCSC_matrix.ivsparse", ivcsc_image(a, 3));
+    return true;
+}
+
+//[[Rcpp::export]]
+Rcpp::List read_IVSparse_slots() {  // the dgCMatrix slots of IVCSC_matrix.ivsparse (read_IVSparse wraps them into a dgCMatrix)
+    FILE* fp = std::fopen("IVCSC_matrix.ivsparse", "rb");
+    if (!fp) Rcpp::stop("cannot open IVCSC_matrix.ivsparse");
+    std::fseek(fp, 0, SEEK_END);
+    const long bytes = std::ftell(fp);
+    std::fseek(fp, 0, SEEK_SET);
+    std::vector<unsigned char> img((size_t)bytes);
+    if (std::fread(img.data(), 1, img.size(), fp) != img.size()) Rcpp::stop("short read");
+    std::fclose(fp);
+    int32_t level = 0, vb = 0;
+    int64_t nrow = 0, ncol = 0, nnz = 0;
+    check(sgl_ivsparse_info(img.data(), (uint64_t)img.size(), &level, &nrow, &ncol, &nnz, &vb));
+    Rcpp::IntegerVector p((int)ncol + 1), i((int)nnz), dim(2);
+    Rcpp::NumericVector x((int)nnz);
+    if (sgl_ivsparse_decode(img.data(), (uint64_t)img.size(), 0, ncol, p.begin(), i.begin(), x.begin(), nnz) < 0) Rcpp::stop(sgl_last_error());
+    dim[0] = (int)nrow;
+    dim[1] = (int)ncol;
+    return Rcpp::List::create(Rcpp::Named("p") = p, Rcpp::Named("i") = i, Rcpp::Named("x") = x, Rcpp::Named("Dim") = dim);
+}
+
+//[[Rcpp::export]]
+Rcpp::List run_nmf_on_sparsematrix_list(Rcpp::List A_, const double tol, const uint16_t maxit, const bool verbose, const uint16_t threads,
+                                        Eigen::MatrixXd w, bool use_vcsc = false, const double L1 = 0, const double L2 = 0) {
+    // the reference packs the list into one IVCSC / VCSC matrix of FLOAT values (:790-822) and runs plain ALS on it (:946-995):
+    // narrow the values through the codec, then fit the decoded chunks (t(A) is built on the device)
+    std::vector<Rcpp::SparseMatrix> A = as_list(A_);
+    std::vector<sgl_csc> a = views(A);
+    std::vector<unsigned char> img = ivcsc_image(a, use_vcsc ? 2 : 3);
+    std::vector<std::vector<int32_t>> P(a.size()), I(a.size());
+    std::vector<std::vector<double>> X(a.size());
+    std::vector<sgl_csc> chunks(a.size());
+    int64_t col0 = 0;
+    for (size_t q = 0; q < a.size(); ++q) {
+        P[q].resize((size_t)a[q].ncol + 1);
+        const int64_t nnz = sgl_ivsparse_decode(img.data(), (uint64_t)img.size(), col0, a[q].ncol, P[q].data(), nullptr, nullptr, 0);
+        if (nnz < 0) Rcpp::stop(sgl_last_error());
+        I[q].resize((size_t)nnz);
+        X[q].resize((size_t)nnz);
+        if (sgl_ivsparse_decode(img.data(), (uint64_t)img.size(), col0, a[q].ncol, P[q].data(), I[q].data(), X[q].data(), nnz) < 0)
+            Rcpp::stop(sgl_last_error());
+        chunks[q] = sgl_csc{a[q].nrow, a[q].ncol, P[q].data(), I[q].data(), X[q].data()};
+        col0 += a[q].ncol;
+    }
+    return nmf_impl(chunks, {}, tol, maxit, verbose, L1, L1, L2, L2, w);
 }
