@@ -49,11 +49,17 @@ bf16_split_kernel(const float* __restrict__ F, int64_t n, uint16_t* __restrict__
     }
 }
 
-template <int KP>
+// PLANES = 2: the BF16 hi | mid pairs above (FP32-equivalent corrections). PLANES = 1: ONE pass over the FP16 shadow of the
+// factor that the 16-bit-operand SpMM of the same half-iteration has just built (spmm_h16.cuh: half(F * 2^se), [rows][KP]) --
+// half the gathered bytes and half the MMAs; used where the precision policy already stages the sparse product's operands in
+// 16 bits (large matrices, sgl_set_precision): an 11-bit operand perturbs G_M -- 5 % of a -- by ~1e-5, far below the 1.6e-4 the
+// 16-bit product leaves in the right-hand sides.
+template <int KP, int PLANES = 2>
 struct GramCorrCfg {
     static_assert(KP == 16 || KP == 32, "tensor-core Gram correction: padded ranks 16 and 32");
+    static_assert(PLANES == 2 || (PLANES == 1 && KP == 32), "the FP16 shadow exists for padded ranks >= 32");
     static constexpr int MT = KP / 16, NT = KP / 8;     // 16-row and 8-column tiles of the KP x KP output
-    static constexpr int EB = KP * 4;                   // bytes of one gathered entry: hi row | mid row, as it lies in global memory
+    static constexpr int EB = KP * 2 * PLANES;          // bytes of one gathered entry as it lies in global memory (hi row | mid row)
     static constexpr int CPE = EB / 16;                 // 16-byte chunks per entry (8 / 4)
     static constexpr int EPL = 128 / EB;                // entries per 128-byte line of the ring (1 / 2)
     static constexpr int SW_MASK = CPE - 1;             // chunk c of entry e sits at chunk ((e % EPL) * CPE + c) ^ ((e / EPL) & SW_MASK) of
@@ -68,7 +74,7 @@ struct GramCorrCfg {
     __host__ __device__ static constexpr uint32_t offset(int e, int c) {  // byte offset of chunk c of entry e inside a stage
         return (uint32_t)((e / EPL) * 128 + ((((e % EPL) * CPE + c) ^ ((e / EPL) & SW_MASK)) * 16));
     }
-    static_assert(WARP_BYTES >= KP * (KP + 1) * 4, "the transpose scratch reuses the ring");
+    static_assert(PLANES == 1 || WARP_BYTES >= KP * (KP + 1) * 4, "the transpose scratch reuses the ring");
 };
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -79,15 +85,21 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint3
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
 // gm[(col - col0) * KP * KP + i * KP + j] = G_M(col)[i][j] for col0 <= col < col0 + ncols (columns without non-zeros are
 // skipped like in the solver: :444). pairs: the BF16 hi / mid planes of the gather factor, [rows][2][KP].
-template <int KP>
-__global__ void __launch_bounds__(GramCorrCfg<KP>::WARPS * 32)
+// PLANES = 1: `pairs` is the FP16 shadow [rows][KP] and inv_scale[0] = 2^-se its inverse scale (device): G_M = D1 * 2^-2se.
+template <int KP, int PLANES>
+__global__ void __launch_bounds__(GramCorrCfg<KP, PLANES>::WARPS * 32)
 gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restrict__ colptr,
                      const int64_t* __restrict__ mptr, const uint2* __restrict__ mrec, int64_t col0, int64_t ncols,
-                     float* __restrict__ gm) {
-    using C = GramCorrCfg<KP>;
+                     float* __restrict__ gm, const float* __restrict__ inv_scale) {
+    using C = GramCorrCfg<KP, PLANES>;
     constexpr int MT = C::MT, NT = C::NT;
     __shared__ __align__(128) unsigned char ring_mem[C::WARPS][C::WARP_BYTES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,13 +112,16 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
     const int nblk = (n + C::BLK - 1) / C::BLK;
     const uint32_t ring = smem_u32(&ring_mem[warp][0]);
 
-    float d1[MT][NT][4], d2[MT][NT][4];
+    float d1[MT][NT][4], d2[PLANES == 2 ? MT : 1][PLANES == 2 ? NT : 1][4];
 #pragma unroll
     for (int p = 0; p < MT; ++p)
 #pragma unroll
         for (int q = 0; q < NT; ++q)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { d1[p][q][c] = 0.f; d2[p][q][c] = 0.f; }
+            for (int c = 0; c < 4; ++c) {
+                d1[p][q][c] = 0.f;
+                if constexpr (PLANES == 2) d2[p][q][c] = 0.f;
+            }
 
     // A block is 16 entries of 4 * KP contiguous bytes (hi row | mid row). One cp.async instruction copies 32 / CPE whole
     // entries, CPE adjacent lanes covering the bytes of one entry in order, so that every request of the instruction is made
@@ -126,7 +141,7 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
             const int e = q * EPI + lane / CPE;
             const uint32_t row = __shfl_sync(0xffffffffu, idxreg, e);
             const bool ok = blk * C::BLK + e < n;  // entries past the end are zero-filled: they add nothing
-            const uint16_t* src = pairs + (int64_t)row * (2 * KP) + chunk * 8;
+            const uint16_t* src = pairs + (int64_t)row * (PLANES * KP) + chunk * 8;
             const uint32_t dst = ring + (uint32_t)(stage * C::STAGE_BYTES) + C::offset(e, chunk);
             cp_async16(dst, src, ok ? 16u : 0u);
         }
@@ -162,14 +177,18 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
         for (int j = 0; j < NT / 2; ++j) {
             ldmatrix_x4_trans(st + C::offset(la_e, 2 * j + la_q), Ah[j][0], Ah[j][1], Ah[j][2], Ah[j][3]);
             ldmatrix_x4_trans(st + C::offset(lm_e, 2 * j + lm_q), Bh[j][0], Bh[j][1], Bh[j][2], Bh[j][3]);
-            ldmatrix_x4_trans(st + C::offset(lm_e, CPE / 2 + 2 * j + lm_q), Bm[j][0], Bm[j][1], Bm[j][2], Bm[j][3]);
+            if constexpr (PLANES == 2) ldmatrix_x4_trans(st + C::offset(lm_e, CPE / 2 + 2 * j + lm_q), Bm[j][0], Bm[j][1], Bm[j][2], Bm[j][3]);
         }
 #pragma unroll
         for (int p = 0; p < MT; ++p)
 #pragma unroll
             for (int q = 0; q < NT; ++q) {
-                mma_bf16_16816(d1[p][q], Ah[p][0], Ah[p][1], Ah[p][2], Ah[p][3], Bh[q / 2][2 * (q & 1)], Bh[q / 2][2 * (q & 1) + 1]);
-                mma_bf16_16816(d2[p][q], Ah[p][0], Ah[p][1], Ah[p][2], Ah[p][3], Bm[q / 2][2 * (q & 1)], Bm[q / 2][2 * (q & 1) + 1]);
+                if constexpr (PLANES == 2) {
+                    mma_bf16_16816(d1[p][q], Ah[p][0], Ah[p][1], Ah[p][2], Ah[p][3], Bh[q / 2][2 * (q & 1)], Bh[q / 2][2 * (q & 1) + 1]);
+                    mma_bf16_16816(d2[p][q], Ah[p][0], Ah[p][1], Ah[p][2], Ah[p][3], Bm[q / 2][2 * (q & 1)], Bm[q / 2][2 * (q & 1) + 1]);
+                } else {
+                    mma_f16_16816(d1[p][q], Ah[p][0], Ah[p][1], Ah[p][2], Ah[p][3], Bh[q / 2][2 * (q & 1)], Bh[q / 2][2 * (q & 1) + 1]);
+                }
             }
         __syncwarp();  // every lane has read the stage
         issue(b + C::STAGES, b % C::STAGES, idx_mine);
@@ -183,10 +202,22 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
     }
     cp_async_wait<0>();
     __syncwarp();
+    const int g = lane >> 2, t = lane & 3;
+    float* out = gm + cl * (int64_t)(KP * KP);
+    if constexpr (PLANES == 1) {
+        const float sc2 = inv_scale[0] * inv_scale[0];
+#pragma unroll
+        for (int p = 0; p < MT; ++p)
+#pragma unroll
+            for (int q = 0; q < NT; ++q) {
+                const int i = 16 * p + g, j = 8 * q + 2 * t;
+                *reinterpret_cast<float2*>(out + i * KP + j) = make_float2(d1[p][q][0] * sc2, d1[p][q][1] * sc2);
+                *reinterpret_cast<float2*>(out + (i + 8) * KP + j) = make_float2(d1[p][q][2] * sc2, d1[p][q][3] * sc2);
+            }
+    } else {
     // G_M = D1 + D2 + D2^T: D2 goes through the ring transposed (row stride KP + 1: the four t-lanes of a row group hit
     // different banks)
     float* sc = reinterpret_cast<float*>(&ring_mem[warp][0]);
-    const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int p = 0; p < MT; ++p)
 #pragma unroll
@@ -198,7 +229,6 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
             sc[(j + 1) * (KP + 1) + i + 8] = d2[p][q][3];
         }
     __syncwarp();
-    float* out = gm + cl * (int64_t)(KP * KP);
 #pragma unroll
     for (int p = 0; p < MT; ++p)
 #pragma unroll
@@ -211,6 +241,7 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
             *reinterpret_cast<float2*>(out + i * KP + j) = make_float2(v0, v1);
             *reinterpret_cast<float2*>(out + (i + 8) * KP + j) = make_float2(v2, v3);
         }
+    }
 }
 
 }  // namespace sgl

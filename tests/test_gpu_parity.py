@@ -273,6 +273,24 @@ def test_tensor_core_gram_correction_matches_fp32_and_oracle(handle, oracle, mon
     assert np.allclose(mma["test_mse"], ffma["test_mse"], rtol=2e-5)
     assert np.allclose(mma["d"], ffma["d"], rtol=1e-3)
     assert not np.array_equal(mma["w"], ffma["w"])  # and they ARE different code paths
+    if k > 16:
+        # where the precision policy stages the sparse product in 16 bits (forced here on a small matrix), the correction is ONE
+        # tensor pass over the product's FP16 shadow of the factor; SGL_GRAMCORR=split keeps the two-pass BF16 split
+        handle.set_precision("mixed16_always")
+        try:
+            one = api.c_ard_nmf(*args)
+            monkeypatch.setenv("SGL_GRAMCORR", "split")
+            two = api.c_ard_nmf(*args)
+            monkeypatch.delenv("SGL_GRAMCORR")
+        finally:
+            handle.set_precision("mixed16")
+        assert not np.array_equal(one["w"], two["w"])
+        for dev in (one, two):
+            assert list(dev["iter"]) == list(ref["iter"])
+            assert np.allclose(dev["test_mse"], ref["test_mse"], rtol=MSE_RTOL)
+            perm = match_factors(ref["w"], dev["w"])
+            assert min_factor_cor(ref["w"], dev["w"], perm) >= COR_MIN and min_factor_cor(ref["h"], dev["h"], perm) >= COR_MIN
+        assert np.allclose(one["test_mse"], two["test_mse"], rtol=2e-5)
 
 
 def test_ard_overfit_break(handle, oracle):
