@@ -192,6 +192,61 @@ nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
         if (!__any_sync(0xffffffffu, any)) break;
 
         // ---- one sweep (src/singlet.cpp:231-248) for every slot that holds a column ----
+        if constexpr (NCL == 1 && KP >= 64) {
+            // One column per lane leaves ONE dependency chain per thread (b_i -> diff -> m -> b) and the in-order warp waits on
+            // it at every coordinate (FP32 pipe 52 % busy, the FFMA / FSEL at the head of the chain hold 29 % of the stall
+            // samples -- profiles/r2_summary.md; reading half of each Gram row from shared memory instead of constant memory
+            // was tried first: -1.6 % with 8 pairs, +7.5 % with 16). Two coordinates per block: m_i, then b_{i+1} updated by a single scalar FMA,
+            // then m_{i+1}; only then are both rank-1 updates applied to all of b, in coordinate order (bit-identical to
+            // step-by-step), so that the next block's chain has 2 x KP/2 independent FFMA2 to hide behind.
+            // x of the next block is read one block ahead, the two reciprocals of the tol bookkeeping are issued before the
+            // rank-1 updates and consumed after them (the in-order warp otherwise waits on LDS / MUFU results -- short
+            // scoreboard was the top stall -- in front of 64 independent FFMA2)
+            float xp0 = sx[threadIdx.x], xp1 = sx[NT + threadIdx.x];
+#pragma unroll
+            for (int i = 0; i < KP; i += 2) {
+                if (i + 1 < k) {  // uniform
+                    const float x0 = xp0, x1 = xp1;
+                    if (i + 2 < KP) { xp0 = sx[(i + 2) * NT + threadIdx.x]; xp1 = sx[((i + 3 < KP) ? i + 3 : i + 2) * NT + threadIdx.x]; }
+                    // the arithmetic of cd_step_nb, twice, with the tol part deferred
+                    const float d0 = fmaf(L2, x0, fmaf(b[0][i >> 1].x, c_inv_diag[i], -L1));
+                    const bool cl0 = (-d0 > x0);
+                    const float xs0 = x0 + d0;
+                    const float m0 = cl0 ? x0 : -d0;
+                    const float b1 = fmaf(c_gram[i * KP + i + 1], m0, b[0][i >> 1].y);
+                    const float d1 = fmaf(L2, x1, fmaf(b1, c_inv_diag[i + 1], -L1));
+                    const bool cl1 = (-d1 > x1);
+                    const float xs1 = x1 + d1;
+                    const float m1 = cl1 ? x1 : -d1;
+                    float r0, r1;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(xs0 + 1e-15f));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(xs1 + 1e-15f));
+                    const float2 mm0 = make_float2(m0, m0), mm1 = make_float2(m1, m1);
+                    const float2* a0 = reinterpret_cast<const float2*>(c_gram + i * KP);
+                    const float2* a1 = reinterpret_cast<const float2*>(c_gram + (i + 1) * KP);
+#pragma unroll
+                    for (int j2 = 0; j2 < KP / 2; ++j2) {
+                        b[0][j2] = __ffma2_rn(a0[j2], mm0, b[0][j2]);
+                        b[0][j2] = __ffma2_rn(a1[j2], mm1, b[0][j2]);
+                    }
+                    float tl = tol[0];
+                    tl = cl0 ? ((x0 != 0.f) ? 1.f : tl) : tl + fabsf(d0 * r0);
+                    tl = cl1 ? ((x1 != 0.f) ? 1.f : tl) : tl + fabsf(d1 * r1);
+                    tol[0] = tl;
+                    sx[(i)*NT + threadIdx.x] = cl0 ? 0.f : xs0;
+                    sx[(i + 1) * NT + threadIdx.x] = cl1 ? 0.f : xs1;
+                } else if (i < k) {  // odd rank: the last coordinate alone
+                    float xi = sx[(i)*NT + threadIdx.x], tl = tol[0];
+                    const float mult = cd_step_nb(b[0][i >> 1].x, c_inv_diag[i], xi, L1, L2, tl);
+                    tol[0] = tl;
+                    sx[(i)*NT + threadIdx.x] = xi;
+                    const float2 mm = make_float2(mult, mult);
+                    const float2* ai = reinterpret_cast<const float2*>(c_gram + i * KP);
+#pragma unroll
+                    for (int j2 = 0; j2 < KP / 2; ++j2) b[0][j2] = __ffma2_rn(ai[j2], mm, b[0][j2]);
+                }
+            }
+        } else {
 #pragma unroll
         for (int i = 0; i < KP; ++i) {
             if (i < k) {  // uniform
@@ -213,6 +268,7 @@ nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
                     for (int s = 0; s < NCL; ++s) b[s][j2] = __ffma2_rn(a2, mm[s], b[s][j2]);
                 }
             }
+        }
         }
     }
 }
