@@ -967,26 +967,28 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
         }
         LAUNCH_CHECK(h);
     } else {
-        const char* gc_env = getenv("SGL_GRAMCORR");  // A/B tests: "ffma" = FP32 correction inside the solver, "split" = always the two-pass BF16 split
-        if ((KPV == 16 || KPV == 32) && !(gc_env && gc_env[0] == 'f')) {
+        const char* gc_env = getenv("SGL_GRAMCORR");  // A/B tests: "ffma" = FP32 correction inside the solver, "split" = always the BF16 split
+        if ((KPV == 16 || KPV == 32 || KPV == 64) && !(gc_env && gc_env[0] == 'f')) {
             // Gram corrections on the tensor cores (gramcorr.cuh), a column chunk at a time (KP^2 floats per column), then
-            // the sub-warp solver with the corrections read back instead of accumulated (mptr = nullptr)
+            // the solver with the corrections read back instead of accumulated (mptr = nullptr)
             const int64_t rows_f = mask->X->nrow;  // rows of the gather factor
             const int64_t nel = rows_f * KPV;
             // Where the precision policy stages the sparse product's operands in 16 bits (large matrices, padded rank >= 32), the
             // FP16 shadow of F_in that the product of this same update has just built is the operand: one tensor pass, half the
-            // gathered bytes. Otherwise F_in is split into BF16 hi | mid pairs (two passes, FP32-equivalent).
-            const bool one_pass = KPV == 32 && use_h16(h, KPV, const_cast<sgl_matrix*>(mask->X)) && !(gc_env && gc_env[0] == 's');
+            // gathered bytes. Otherwise F_in is split into BF16 hi | mid pairs (FP32-equivalent).
+            const bool one_pass = KPV >= 32 && use_h16(h, KPV, const_cast<sgl_matrix*>(mask->X)) && !(gc_env && gc_env[0] == 's');
             if (!one_pass) {
                 SGL_TRY(h->bf_pairs.ensure((size_t)nel * 2));
                 int64_t g = (nel / 4 + 255) / 256;
                 if (g > 8 * h->sm_count) g = 8 * h->sm_count;
-                if (KPV == 16) bf16_split_kernel<16><<<(unsigned)(g > 0 ? g : 1), 256, 0, h->stream>>>(F_in, nel, h->bf_pairs.p);
-                else bf16_split_kernel<32><<<(unsigned)(g > 0 ? g : 1), 256, 0, h->stream>>>(F_in, nel, h->bf_pairs.p);
+                const unsigned gg = (unsigned)(g > 0 ? g : 1);
+                if (KPV == 16) bf16_split_kernel<16><<<gg, 256, 0, h->stream>>>(F_in, nel, h->bf_pairs.p);
+                else if (KPV == 32) bf16_split_kernel<32><<<gg, 256, 0, h->stream>>>(F_in, nel, h->bf_pairs.p);
+                else bf16_split_kernel<64><<<gg, 256, 0, h->stream>>>(F_in, nel, h->bf_pairs.p);
                 LAUNCH_CHECK(h);
             }
-            const int G = (KPV == 16) ? MaskedSubCfg<16>::G : MaskedSubCfg<32>::G;
-            const int64_t cols_per_cta = 4 * (int64_t)G;
+            // columns per solver CTA: the sub-warp solver takes 4 groups of G columns, the warp-per-column solver (KP = 64) 4 columns
+            const int64_t cols_per_cta = KPV == 64 ? MaskedCfg<64>::WARPS : 4 * (int64_t)(KPV == 16 ? MaskedSubCfg<16>::G : MaskedSubCfg<32>::G);
             const char* mb_env = getenv("SGL_GRAMCORR_MB");  // chunk budget (tests force several chunks)
             const int64_t budget = (mb_env ? atoll(mb_env) : 1024) << 20;
             int64_t chunk = budget / ((int64_t)KPV * KPV * 4) / cols_per_cta * cols_per_cta;
@@ -996,23 +998,38 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
             SGL_TRY(h->gm.ensure((size_t)chunk * KPV * KPV));
             n_parts = ncol_up / cols_per_cta;
             SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
+            const float* inv_scale = reinterpret_cast<const float*>(h->shadow_meta.p + 1);
+            static bool attr_done_dev[64] = {};
+            if (KPV == 64 && !attr_done_dev[h->device & 63]) {  // 64 KB of dynamic shared memory for the two-plane ring
+                SGL_CUDA(cudaFuncSetAttribute(gram_corr_mma_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              GramCorrCfg<64, 2>::WARPS * GramCorrCfg<64, 2>::WARP_BYTES));
+                attr_done_dev[h->device & 63] = true;
+            }
             for (int64_t c0 = 0; c0 < ncol; c0 += chunk) {
                 const int64_t nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
-                const unsigned cg_grid = (unsigned)((nc + 3) / 4), sv_grid = (unsigned)((nc + cols_per_cta - 1) / cols_per_cta);
+                const unsigned sv_grid = (unsigned)((nc + cols_per_cta - 1) / cols_per_cta);
                 const int64_t blk0 = c0 / cols_per_cta;
+#define GRAMCORR_LAUNCH(KPC, PL, SRC)                                                                                  \
+    gram_corr_mma_kernel<KPC, PL><<<(unsigned)((nc * GramCorrCfg<KPC, PL>::WPC + 3) / 4), 128,                         \
+                                    GramCorrCfg<KPC, PL>::WARPS * GramCorrCfg<KPC, PL>::WARP_BYTES, h->stream>>>(      \
+        SRC, colptr, mask->mptr, mask->mrec, c0, nc, h->gm.p, inv_scale)
                 if (KPV == 16) {
-                    gram_corr_mma_kernel<16, 2><<<cg_grid, 128, 0, h->stream>>>(h->bf_pairs.p, colptr, mask->mptr, mask->mrec, c0, nc, h->gm.p, nullptr);
+                    GRAMCORR_LAUNCH(16, 2, h->bf_pairs.p);
                     nnls_masked_sub_kernel<16, 1><<<sv_grid, 128, 0, h->stream>>>(Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, nullptr,
                                                                                  nullptr, ncol, k, (float)L1, (float)L2, h->part.p, h->gm.p, blk0);
-                } else {
-                    if (one_pass)
-                        gram_corr_mma_kernel<32, 1><<<cg_grid, 128, 0, h->stream>>>(h->shadow.p, colptr, mask->mptr, mask->mrec, c0, nc, h->gm.p,
-                                                                                   reinterpret_cast<const float*>(h->shadow_meta.p + 1));
-                    else
-                        gram_corr_mma_kernel<32, 2><<<cg_grid, 128, 0, h->stream>>>(h->bf_pairs.p, colptr, mask->mptr, mask->mrec, c0, nc, h->gm.p, nullptr);
+                } else if (KPV == 32) {
+                    if (one_pass) GRAMCORR_LAUNCH(32, 1, h->shadow.p);
+                    else GRAMCORR_LAUNCH(32, 2, h->bf_pairs.p);
                     nnls_masked_sub_kernel<32, 1><<<sv_grid, 128, 0, h->stream>>>(Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, nullptr,
                                                                                  nullptr, ncol, k, (float)L1, (float)L2, h->part.p, h->gm.p, blk0);
+                } else {
+                    if (one_pass) GRAMCORR_LAUNCH(64, 1, h->shadow.p);
+                    else GRAMCORR_LAUNCH(64, 2, h->bf_pairs.p);
+                    nnls_masked_kernel<64><<<sv_grid, MaskedCfg<64>::WARPS * 32, 0, h->stream>>>(Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr,
+                                                                                                nullptr, nullptr, ncol, k, (float)L1, (float)L2,
+                                                                                                h->part.p, h->gm.p, blk0);
                 }
+#undef GRAMCORR_LAUNCH
                 LAUNCH_CHECK(h);
             }
         } else if (KPV <= 32) {

@@ -56,13 +56,21 @@ bf16_split_kernel(const float* __restrict__ F, int64_t n, uint16_t* __restrict__
 // 16-bit product leaves in the right-hand sides.
 template <int KP, int PLANES = 2>
 struct GramCorrCfg {
-    static_assert(KP == 16 || KP == 32, "tensor-core Gram correction: padded ranks 16 and 32");
-    static_assert(PLANES == 2 || (PLANES == 1 && KP == 32), "the FP16 shadow exists for padded ranks >= 32");
+    static_assert(KP == 16 || KP == 32 || KP == 64, "tensor-core Gram correction: padded ranks 16, 32 and 64");
+    static_assert(PLANES == 2 || (PLANES == 1 && KP >= 32), "the FP16 shadow exists for padded ranks >= 32");
     static constexpr int MT = KP / 16, NT = KP / 8;     // 16-row and 8-column tiles of the KP x KP output
+    // KP = 64: the 64 x 64 output does not fit one warp's registers; WPC = 2 warps share a column, each owning MTW = 2 of
+    // the four 16-row tiles (both gather the whole list: the B operand needs every factor). With the output split, D2^T
+    // would live in the other warp, so the split path adds the third pass (mid^T hi) into the SAME accumulator instead of
+    // transposing: G_M = hi^T hi + hi^T mid + mid^T hi.
+    static constexpr int WPC = (KP + 31) / 32 > 1 ? KP / 32 : 1;
+    static constexpr int MTW = MT / WPC;
+    static constexpr bool THREE_PASS = (WPC > 1) && (PLANES == 2);
     static constexpr int EB = KP * 2 * PLANES;          // bytes of one gathered entry as it lies in global memory (hi row | mid row)
     static constexpr int CPE = EB / 16;                 // 16-byte chunks per entry (8 / 4)
-    static constexpr int EPL = 128 / EB;                // entries per 128-byte line of the ring (1 / 2)
-    static constexpr int SW_MASK = CPE - 1;             // chunk c of entry e sits at chunk ((e % EPL) * CPE + c) ^ ((e / EPL) & SW_MASK) of
+    static constexpr int EPL = (EB >= 128) ? 1 : 128 / EB;  // entries per 128-byte line of the ring
+    static constexpr int LPE = (EB >= 128) ? EB / 128 : 1;  // lines per entry (2 at KP = 64 with two planes)
+    static constexpr int SW_MASK = (CPE < 8 ? CPE : 8) - 1; // chunk c of entry e sits at chunk ((e % EPL) * CPE + c) ^ ((e / EPL) & SW_MASK) of
                                                         // line e / EPL: unpadded lines, so the 8 lanes that copy one line with cp.async write
                                                         // one conflict-free wavefront, AND the 8 row addresses of an ldmatrix tile (8
                                                         // consecutive entries, same logical chunk) fall into 8 distinct 16-byte bank groups
@@ -72,9 +80,9 @@ struct GramCorrCfg {
     static constexpr int WARPS = 4;
     static constexpr int WARP_BYTES = STAGES * STAGE_BYTES;
     __host__ __device__ static constexpr uint32_t offset(int e, int c) {  // byte offset of chunk c of entry e inside a stage
-        return (uint32_t)((e / EPL) * 128 + ((((e % EPL) * CPE + c) ^ ((e / EPL) & SW_MASK)) * 16));
+        return (uint32_t)(((e / EPL) * LPE + c / 8) * 128 + (((((e % EPL) * CPE + c) % 8) ^ ((e / EPL) & SW_MASK)) * 16));
     }
-    static_assert(PLANES == 1 || WARP_BYTES >= KP * (KP + 1) * 4, "the transpose scratch reuses the ring");
+    static_assert(PLANES == 1 || THREE_PASS || WARP_BYTES >= KP * (KP + 1) * 4, "the transpose scratch reuses the ring");
 };
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -100,19 +108,22 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
                      const int64_t* __restrict__ mptr, const uint2* __restrict__ mrec, int64_t col0, int64_t ncols,
                      float* __restrict__ gm, const float* __restrict__ inv_scale) {
     using C = GramCorrCfg<KP, PLANES>;
-    constexpr int MT = C::MT, NT = C::NT;
-    __shared__ __align__(128) unsigned char ring_mem[C::WARPS][C::WARP_BYTES];
+    constexpr int MT = C::MTW, NT = C::NT;  // MT: the m-tiles of THIS warp
+    extern __shared__ __align__(128) unsigned char ring_dyn[];  // [WARPS][WARP_BYTES] (64 KB at KP = 64 with two planes)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t cl = (int64_t)blockIdx.x * C::WARPS + warp;
+    const int64_t cl = ((int64_t)blockIdx.x * C::WARPS + warp) / C::WPC;
+    const int mt0 = ((int)(warp % C::WPC)) * MT;  // first m-tile of this warp (KP = 64: rows 0-31 or 32-63 of the output)
     if (cl >= ncols) return;  // warp-uniform; no CTA-wide barrier below
     const int64_t col = col0 + cl;
     if (colptr[col] == colptr[col + 1]) return;
     const int64_t mb = mptr[col];
     const int n = (int)(mptr[col + 1] - mb);
     const int nblk = (n + C::BLK - 1) / C::BLK;
-    const uint32_t ring = smem_u32(&ring_mem[warp][0]);
+    unsigned char* ring_mine = ring_dyn + (size_t)warp * C::WARP_BYTES;
+    const uint32_t ring = smem_u32(ring_mine);
 
-    float d1[MT][NT][4], d2[PLANES == 2 ? MT : 1][PLANES == 2 ? NT : 1][4];
+    constexpr bool TWO_ACC = (PLANES == 2) && !C::THREE_PASS;
+    float d1[MT][NT][4], d2[TWO_ACC ? MT : 1][TWO_ACC ? NT : 1][4];
 #pragma unroll
     for (int p = 0; p < MT; ++p)
 #pragma unroll
@@ -120,7 +131,7 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 d1[p][q][c] = 0.f;
-                if constexpr (PLANES == 2) d2[p][q][c] = 0.f;
+                if constexpr (TWO_ACC) d2[p][q][c] = 0.f;
             }
 
     // A block is 16 entries of 4 * KP contiguous bytes (hi row | mid row). One cp.async instruction copies 32 / CPE whole
@@ -172,10 +183,15 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
         __syncwarp();
         const uint32_t st = ring + (uint32_t)((b % C::STAGES) * C::STAGE_BYTES);
         // P[q] = {F[2t][8q+g], F[2t+1][8q+g]}, Q[q] = the same for entries 8 + 2t, 9 + 2t  (g = lane / 4, t = lane % 4)
-        uint32_t Ah[MT][4], Bh[NT / 2][4], Bm[NT / 2][4];
+        uint32_t Ah[MT][4], Am[C::THREE_PASS ? MT : 1][4], Bh[NT / 2][4], Bm[PLANES == 2 ? NT / 2 : 1][4];
+#pragma unroll
+        for (int pl = 0; pl < MT; ++pl) {
+            ldmatrix_x4_trans(st + C::offset(la_e, 2 * (mt0 + pl) + la_q), Ah[pl][0], Ah[pl][1], Ah[pl][2], Ah[pl][3]);
+            if constexpr (C::THREE_PASS)
+                ldmatrix_x4_trans(st + C::offset(la_e, CPE / 2 + 2 * (mt0 + pl) + la_q), Am[pl][0], Am[pl][1], Am[pl][2], Am[pl][3]);
+        }
 #pragma unroll
         for (int j = 0; j < NT / 2; ++j) {
-            ldmatrix_x4_trans(st + C::offset(la_e, 2 * j + la_q), Ah[j][0], Ah[j][1], Ah[j][2], Ah[j][3]);
             ldmatrix_x4_trans(st + C::offset(lm_e, 2 * j + lm_q), Bh[j][0], Bh[j][1], Bh[j][2], Bh[j][3]);
             if constexpr (PLANES == 2) ldmatrix_x4_trans(st + C::offset(lm_e, CPE / 2 + 2 * j + lm_q), Bm[j][0], Bm[j][1], Bm[j][2], Bm[j][3]);
         }
@@ -183,7 +199,11 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
         for (int p = 0; p < MT; ++p)
 #pragma unroll
             for (int q = 0; q < NT; ++q) {
-                if constexpr (PLANES == 2) {
+                if constexpr (C::THREE_PASS) {
+                    mma_bf16_16816(d1[p][q], Ah[p][0], Ah[p][1], Ah[p][2], Ah[p][3], Bh[q / 2][2 * (q & 1)], Bh[q / 2][2 * (q & 1) + 1]);
+                    mma_bf16_16816(d1[p][q], Ah[p][0], Ah[p][1], Ah[p][2], Ah[p][3], Bm[q / 2][2 * (q & 1)], Bm[q / 2][2 * (q & 1) + 1]);
+                    mma_bf16_16816(d1[p][q], Am[p][0], Am[p][1], Am[p][2], Am[p][3], Bh[q / 2][2 * (q & 1)], Bh[q / 2][2 * (q & 1) + 1]);
+                } else if constexpr (PLANES == 2) {
                     mma_bf16_16816(d1[p][q], Ah[p][0], Ah[p][1], Ah[p][2], Ah[p][3], Bh[q / 2][2 * (q & 1)], Bh[q / 2][2 * (q & 1) + 1]);
                     mma_bf16_16816(d2[p][q], Ah[p][0], Ah[p][1], Ah[p][2], Ah[p][3], Bm[q / 2][2 * (q & 1)], Bm[q / 2][2 * (q & 1) + 1]);
                 } else {
@@ -204,20 +224,20 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
     __syncwarp();
     const int g = lane >> 2, t = lane & 3;
     float* out = gm + cl * (int64_t)(KP * KP);
-    if constexpr (PLANES == 1) {
-        const float sc2 = inv_scale[0] * inv_scale[0];
+    if constexpr (!TWO_ACC) {
+        const float sc2 = (PLANES == 1) ? inv_scale[0] * inv_scale[0] : 1.f;
 #pragma unroll
         for (int p = 0; p < MT; ++p)
 #pragma unroll
             for (int q = 0; q < NT; ++q) {
-                const int i = 16 * p + g, j = 8 * q + 2 * t;
+                const int i = 16 * (mt0 + p) + g, j = 8 * q + 2 * t;
                 *reinterpret_cast<float2*>(out + i * KP + j) = make_float2(d1[p][q][0] * sc2, d1[p][q][1] * sc2);
                 *reinterpret_cast<float2*>(out + (i + 8) * KP + j) = make_float2(d1[p][q][2] * sc2, d1[p][q][3] * sc2);
             }
     } else {
     // G_M = D1 + D2 + D2^T: D2 goes through the ring transposed (row stride KP + 1: the four t-lanes of a row group hit
     // different banks)
-    float* sc = reinterpret_cast<float*>(&ring_mem[warp][0]);
+    float* sc = reinterpret_cast<float*>(ring_mine);
 #pragma unroll
     for (int p = 0; p < MT; ++p)
 #pragma unroll

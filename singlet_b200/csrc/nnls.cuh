@@ -356,13 +356,16 @@ nnls_masked_kernel(const float* __restrict__ Bparts, int splits, float* __restri
                    const int64_t* __restrict__ colptr, // X's column pointers (empty-column skip)
                    const int64_t* __restrict__ mptr,   // [ncol + 1] held-out list pointers
                    const uint2* __restrict__ mrec,     // held-out records {row, value bits}
-                   int64_t ncol, int k, float L1, float L2, double* __restrict__ rowsum_part)
+                   int64_t ncol, int k, float L1, float L2, double* __restrict__ rowsum_part,
+                   // corrections computed beforehand on the tensor cores (gramcorr.cuh), see nnls_masked_sub_kernel
+                   const float* __restrict__ gm = nullptr, int64_t blk0 = 0)
 {
     constexpr int RPL = MaskedCfg<KP>::RPL;
     constexpr int WARPS = MaskedCfg<KP>::WARPS;
     __shared__ double sred[WARPS][KP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t col = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t blk = (int64_t)blockIdx.x + blk0;
+    const int64_t col = blk * WARPS + warp;
     const bool in_range = col < ncol;
     const bool solve = in_range && (colptr[col] != colptr[col + 1]);
 
@@ -384,7 +387,21 @@ nnls_masked_kernel(const float* __restrict__ Bparts, int splits, float* __restri
 
     if (solve) {
         // correction G_M = sum over held-out rows of f f^T  (reference: AAt(submat(w, idx)), :460-461)
-        const int64_t mb = mptr[col], me = mptr[col + 1];
+        if (gm != nullptr) {  // precomputed: rows lane and lane + 32 of this column's KP x KP block
+            const float* src = gm + (col - blk0 * WARPS) * (int64_t)(KP * KP);
+#pragma unroll
+            for (int c = 0; c < RPL; ++c) {
+                const int r = lane + 32 * c;
+                if (r < KP) {
+#pragma unroll
+                    for (int i4 = 0; i4 < KP / 4; ++i4) {
+                        const float4 v = *reinterpret_cast<const float4*>(src + r * KP + 4 * i4);
+                        a[c][4 * i4 + 0] = v.x; a[c][4 * i4 + 1] = v.y; a[c][4 * i4 + 2] = v.z; a[c][4 * i4 + 3] = v.w;
+                    }
+                }
+            }
+        }
+        const int64_t mb = gm ? 0 : mptr[col], me = gm ? 0 : mptr[col + 1];
         for (int64_t p = mb; p < me; ++p) {
             const int64_t row = (int64_t)mrec[p].x;
             const float* fr = F + row * KP;
@@ -481,7 +498,7 @@ nnls_masked_kernel(const float* __restrict__ Bparts, int splits, float* __restri
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) s += sred[w][t];
-        rowsum_part[(int64_t)blockIdx.x * KP + t] = s;
+        rowsum_part[blk * KP + t] = s;
     }
 }
 

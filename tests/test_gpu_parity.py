@@ -240,10 +240,10 @@ def test_ard_nmf_matches_oracle(handle, oracle, k, maxit, trace):
     assert abs(tr_dev - tr_ref) <= MSE_RTOL * tr_ref
 
 
-@pytest.mark.parametrize("k", [12, 16, 20, 32])
+@pytest.mark.parametrize("k", [12, 16, 20, 32, 40, 64])
 def test_tensor_core_gram_correction_matches_fp32_and_oracle(handle, oracle, monkeypatch, k):
     """The masked solver's per-column correction a_i = a - W_M W_M^T (src/singlet.cpp:460-462) on the tensor cores (gramcorr.cuh:
-    two BF16-split mma passes, the default for padded ranks 16 / 32) against the FP32 FFMA accumulation inside the solver
+    BF16-split mma passes, the default for padded ranks 16 / 32 / 64) against the FP32 FFMA accumulation inside the solver
     (SGL_GRAMCORR=ffma) and against the FP64 oracle; cutting the columns into many chunks (SGL_GRAMCORR_MB=0: one CTA's
     columns per chunk) must not change a bit."""
     from singlet_b200 import api, synth
