@@ -941,6 +941,9 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
                     //  round to the sub-warp kernel would cost 0.17 ms for 11,400 columns against the 0.33 ms it replaces)
                     // (14 one-warp CTAs per SM -- __launch_bounds__(32, 14), which ptxas answers with a 128-register build -- so that
                     //  125,000 columns make one round: 1.086 vs 1.068 ms, no gain either)
+                    // (tail split -- full rounds on the two-column kernel, the remainder on the one-column-per-lane variant: 1.075 vs
+                    //  1.075 ms on the 125,000-column shard and 1.69 vs 1.52 ms on the 250,000-column one. The tail costs one
+                    //  column LATENCY, 3200 dependent coordinate steps x ~100 clk = 0.33 ms, whatever the lane holds)
                     if (false) {}
                     else if (ncol >= (int64_t)h->sm_count * 128 * 2) NNLS_LAUNCH(32, 128, 2)
                     else NNLS_LAUNCH(32, 32, 1)
