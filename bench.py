@@ -23,7 +23,7 @@ scaling is "strong". Rank 0 prints ONE JSON line.
   cores, on bounded column samples of the same workload: warm iterations are timed at TWO sample sizes, the time per
   iteration is fitted as a * cells + b (b = the m NNLS solves of the W update, which do not scale with the cell count)
   and evaluated at the full cell count. The reference arm imports nothing of singlet_b200 (no CUDA library is loaded).
-* ``c1_run_nmf`` / ``cv_sweep`` / ``c4_ard_nmf`` (N = 1): BASELINE's other configs through the public API -- the second
+* ``c1_run_nmf`` / ``cv_sweep`` / ``c4_ard_nmf`` / ``masked_als`` (N = 1): BASELINE's other configs through the public API -- the second
   half of the metric ("CV rank-sweep wall time") with the reference CPU timed on a sample of the same fits.
 """
 from __future__ import annotations
@@ -503,7 +503,48 @@ def extras_legs(device):
                                             "seconds": cp, "nnz": int(Ap.nnz), "ranks_tried": [int(q) for q in cv["k"].unique()],
                                             "best_rank": int(mod["w"].shape[1]), "final_iterations": int(mod["iter"])}
     h.close()
+    # ---- the masked (cross-validation) iteration at scale: c_ard_nmf's loop on a 30k x 100k slice of configs[2], k = 32, with the
+    # per-column Gram corrections on the tensor cores (default) and inside the solver as FP32 FMAs (SGL_GRAMCORR=ffma, round 1) ----
+    res["masked_als"] = masked_als_leg(device)
     return res
+
+
+def masked_als_leg(device, m=30000, n=100000, dens=0.05, k=32, steps=5, warmup=3):
+    from singlet_b200 import synth
+    from singlet_b200.multi import RankComm, RankFit
+    from singlet_b200.sharded import CudaBackend
+
+    out = {"workload": f"masked ALS iteration (predict_mask both ways + scale + cor, src/singlet.cpp:1091-1152) on synthetic {m} x {n}, "
+                       f"{dens:.0%}, k = {k}, 1/20 held out, through sgl_fit_iterate", "held_out_entries_per_half_iteration": m * n // 20}
+    for name, env in (("tensor_core_correction", None), ("fp32_ffma_correction", "ffma")):
+        if env is None:
+            os.environ.pop("SGL_GRAMCORR", None)
+        else:
+            os.environ["SGL_GRAMCORR"] = env
+        be = CudaBackend(device)
+        try:
+            table = synth.values_table(m, dens)
+            A_sh = be.synth(m, n, dens, synth.DATA_SEED, 0, 0, n, table)
+            At_sh = be.synth(m, n, dens, synth.DATA_SEED, 1, 0, m, table)
+            comm = RankComm(be._h, device, 1, 0, None)
+            fit = RankFit(comm, A_sh, At_sh, n, k, synth.w_init(k, m), masked=True, seed=4321, inv_density=20)
+            for _ in range(warmup):
+                fit.iterate(L1, L1, L2, L2)
+            be.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fit.iterate(L1, L1, L2, L2)  # synchronises (tol is read back every iteration)
+            ms = (time.perf_counter() - t0) * 1000.0 / steps
+            t0 = time.perf_counter()
+            mse = fit.test_mse()
+            ms_mse = (time.perf_counter() - t0) * 1000.0
+            out[name] = {"ms_per_iteration": ms, "mse_test_ms": ms_mse, "test_mse": mse}
+            fit.close()
+            comm.close()
+        finally:
+            be.close()
+            os.environ.pop("SGL_GRAMCORR", None)
+    return out
 
 
 def planted_counts(m, n, rank, density, seed):
