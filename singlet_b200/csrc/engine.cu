@@ -115,6 +115,8 @@ struct sgl_handle {
     // FP16 shadow of the gather operand of the SpMM in flight (spmm_h16.cuh) + {max |F| bits, 2^-se}
     DevBuf<uint16_t> shadow;
     DevBuf<uint32_t> shadow_meta;
+    const float* shadow_src = nullptr;  // the factor the shadow was last built from (stream-ordered with its users)
+    int shadow_kp = 0;
     int precision = SGL_PRECISION_MIXED16;
     DevBuf<double> part, scal, losses, gram_w;
     // tensor-core Gram correction (gramcorr.cuh): BF16 hi / mid pairs of the gather factor, G_M of a column chunk
@@ -781,6 +783,8 @@ static int build_shadow(sgl_handle* h, const float* F, int64_t rows, int KPV) {
     shadow_kernel<<<(unsigned)grid, 256, 0, h->stream>>>(F, n, h->shadow_meta.p, reinterpret_cast<__half*>(h->shadow.p),
                                                         reinterpret_cast<float*>(h->shadow_meta.p + 1));
     LAUNCH_CHECK(h);
+    h->shadow_src = F;  // whose shadow this is: the masked solver's single-pass Gram correction reuses it only for the same factor
+    h->shadow_kp = KPV;
     return SGL_OK;
 }
 
@@ -979,7 +983,8 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
             // Where the precision policy stages the sparse product's operands in 16 bits (large matrices, padded rank >= 32), the
             // FP16 shadow of F_in that the product of this same update has just built is the operand: one tensor pass, half the
             // gathered bytes. Otherwise F_in is split into BF16 hi | mid pairs (FP32-equivalent).
-            const bool one_pass = KPV >= 32 && use_h16(h, KPV, const_cast<sgl_matrix*>(mask->X)) && !(gc_env && gc_env[0] == 's');
+            const bool one_pass = KPV >= 32 && use_h16(h, KPV, const_cast<sgl_matrix*>(mask->X)) && !(gc_env && gc_env[0] == 's') &&
+                                  h->shadow_src == F_in && h->shadow_kp == KPV;  // the product of THIS update built it from F_in
             if (!one_pass) {
                 SGL_TRY(h->bf_pairs.ensure((size_t)nel * 2));
                 int64_t g = (nel / 4 + 255) / 256;
