@@ -1033,9 +1033,15 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
                 } else {
                     if (one_pass) GRAMCORR_LAUNCH(64, 1, h->shadow.p);
                     else GRAMCORR_LAUNCH(64, 2, h->bf_pairs.p);
-                    nnls_masked_kernel<64><<<sv_grid, MaskedCfg<64>::WARPS * 32, 0, h->stream>>>(Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr,
-                                                                                                nullptr, nullptr, ncol, k, (float)L1, (float)L2,
-                                                                                                h->part.p, h->gm.p, blk0);
+                    const char* m64 = getenv("SGL_MASKED64");  // "old": the step-by-step warp-per-column sweep (A/B tests)
+                    if (m64 && m64[0] == 'o')
+                        nnls_masked_kernel<64><<<sv_grid, MaskedCfg<64>::WARPS * 32, 0, h->stream>>>(Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr,
+                                                                                                    nullptr, nullptr, ncol, k, (float)L1, (float)L2,
+                                                                                                    h->part.p, h->gm.p, blk0);
+                    else
+                        nnls_masked64_blocked_kernel<<<sv_grid, MaskedCfg<64>::WARPS * 32, 0, h->stream>>>(Bparts, splits, F_out, h->gram_f_nojit.p, F_in,
+                                                                                                          colptr, nullptr, nullptr, ncol, k, (float)L1,
+                                                                                                          (float)L2, h->part.p, h->gm.p, blk0);
                 }
 #undef GRAMCORR_LAUNCH
                 LAUNCH_CHECK(h);
@@ -1083,7 +1089,17 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
             Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, mask->mptr, mask->mrec, ncol, k, (float)L1, \
             (float)L2, h->part.p);                                                                                  \
         break;
-                MASKED_CASE(4) MASKED_CASE(8) MASKED_CASE(16) MASKED_CASE(32) MASKED_CASE(64)
+                MASKED_CASE(4) MASKED_CASE(8) MASKED_CASE(16) MASKED_CASE(32)
+                case 64: {
+                    const char* m64 = getenv("SGL_MASKED64");
+                    if (m64 && m64[0] == 'o')
+                        nnls_masked_kernel<64><<<(unsigned)n_parts, MaskedCfg<64>::WARPS * 32, 0, h->stream>>>(
+                            Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, mask->mptr, mask->mrec, ncol, k, (float)L1, (float)L2, h->part.p);
+                    else
+                        nnls_masked64_blocked_kernel<<<(unsigned)n_parts, MaskedCfg<64>::WARPS * 32, 0, h->stream>>>(
+                            Bparts, splits, F_out, h->gram_f_nojit.p, F_in, colptr, mask->mptr, mask->mrec, ncol, k, (float)L1, (float)L2, h->part.p,
+                            nullptr, 0);
+                } break;
                 default: break;
 #undef MASKED_CASE
             }

@@ -839,6 +839,137 @@ nnls_masked_sub_kernel(const float* __restrict__ Bparts, int splits, float* __re
     }
 }
 
+// Padded rank 64, blocked sweep. Same solve as nnls_masked_kernel<64> (warp per column, the lane holds two rows of a_i) with the
+// rows of a lane CONSECUTIVE (2 lane, 2 lane + 1) so that, as in the sub-warp kernel, the owner lane o runs the two coordinates
+// 2o, 2o + 1 on a private copy of its b entries (phase A), the two multipliers are broadcast by two overlapping shuffles and every
+// lane applies them in coordinate order (phase B) -- bit-identical to the step-by-step order, half the shuffle-bound steps.
+// Padding coordinates (i >= k) are inert: b = x = inv = 0 gives a zero multiplier.
+__global__ void __launch_bounds__(MaskedCfg<64>::WARPS * 32)
+nnls_masked64_blocked_kernel(const float* __restrict__ Bparts, int splits, float* __restrict__ X, const float* __restrict__ gram_f,
+                             const float* __restrict__ F, const int64_t* __restrict__ colptr, const int64_t* __restrict__ mptr,
+                             const uint2* __restrict__ mrec, int64_t ncol, int k, float L1, float L2,
+                             double* __restrict__ rowsum_part, const float* __restrict__ gm, int64_t blk0) {
+    constexpr int KP = 64, WARPS = MaskedCfg<64>::WARPS;
+    __shared__ double sred[WARPS][KP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t blk = (int64_t)blockIdx.x + blk0;
+    const int64_t col = blk * WARPS + warp;
+    const bool in_range = col < ncol;
+    const bool solve = in_range && (colptr[col] != colptr[col + 1]);
+    const int r0 = 2 * lane;  // my rows: r0, r0 + 1
+    float a[2][KP];
+    float b[2] = {0.f, 0.f}, x[2] = {0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < KP; ++i) a[c][i] = 0.f;
+    if (in_range) {
+        for (int s = 0; s < splits; ++s) {
+            const float2 v = *reinterpret_cast<const float2*>(Bparts + ((int64_t)s * ncol + col) * KP + r0);
+            b[0] += v.x;
+            b[1] += v.y;
+        }
+        const float2 v = *reinterpret_cast<const float2*>(X + col * KP + r0);
+        x[0] = v.x;
+        x[1] = v.y;
+    }
+    if (solve) {
+        if (gm != nullptr) {
+            const float* src = gm + (col - blk0 * WARPS) * (int64_t)(KP * KP) + (int64_t)r0 * KP;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i4 = 0; i4 < KP / 4; ++i4) {
+                    const float4 v = *reinterpret_cast<const float4*>(src + c * KP + 4 * i4);
+                    a[c][4 * i4 + 0] = v.x; a[c][4 * i4 + 1] = v.y; a[c][4 * i4 + 2] = v.z; a[c][4 * i4 + 3] = v.w;
+                }
+        } else if (mptr != nullptr) {  // FP32 correction inside the solver (SGL_GRAMCORR=ffma)
+            const int64_t mb = mptr[col], me = mptr[col + 1];
+            for (int64_t p = mb; p < me; ++p) {
+                const float* fr = F + (int64_t)mrec[p].x * KP;
+                const float2 mine = *reinterpret_cast<const float2*>(fr + r0);
+                const float4* fr4 = reinterpret_cast<const float4*>(fr);
+#pragma unroll
+                for (int i4 = 0; i4 < KP / 4; ++i4) {
+                    const float4 f4 = fr4[i4];  // uniform address: broadcast
+                    a[0][4 * i4 + 0] = fmaf(mine.x, f4.x, a[0][4 * i4 + 0]); a[0][4 * i4 + 1] = fmaf(mine.x, f4.y, a[0][4 * i4 + 1]);
+                    a[0][4 * i4 + 2] = fmaf(mine.x, f4.z, a[0][4 * i4 + 2]); a[0][4 * i4 + 3] = fmaf(mine.x, f4.w, a[0][4 * i4 + 3]);
+                    a[1][4 * i4 + 0] = fmaf(mine.y, f4.x, a[1][4 * i4 + 0]); a[1][4 * i4 + 1] = fmaf(mine.y, f4.y, a[1][4 * i4 + 1]);
+                    a[1][4 * i4 + 2] = fmaf(mine.y, f4.z, a[1][4 * i4 + 2]); a[1][4 * i4 + 3] = fmaf(mine.y, f4.w, a[1][4 * i4 + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i4 = 0; i4 < KP / 4; ++i4) {
+                const float4 v = *reinterpret_cast<const float4*>(gram_f + (r0 + c) * KP + 4 * i4);
+                a[c][4 * i4 + 0] = v.x - a[c][4 * i4 + 0]; a[c][4 * i4 + 1] = v.y - a[c][4 * i4 + 1];
+                a[c][4 * i4 + 2] = v.z - a[c][4 * i4 + 2]; a[c][4 * i4 + 3] = v.w - a[c][4 * i4 + 3];
+            }
+        // my diagonal elements a[c][r0 + c]: picked with selects (the index depends on the lane)
+        float inv[2] = {0.f, 0.f};
+#pragma unroll
+        for (int o = 0; o < 32; ++o) {
+            if (lane == o) {
+                inv[0] = (2 * o < k) ? 1.0f / a[0][2 * o] : 0.f;
+                inv[1] = (2 * o + 1 < k) ? 1.0f / a[1][2 * o + 1] : 0.f;
+            }
+        }
+        float tol = 1.f;
+        const float kf = (float)k;
+        for (int sweep = 0; sweep < NNLS_MAX_SWEEPS && (tol / kf > 1e-8f); ++sweep) {
+            float term[2] = {0.f, 0.f};
+            bool ev[2] = {false, false};
+#pragma unroll
+            for (int o = 0; o < 32; ++o) {
+                if (2 * o < k) {  // uniform: a block with at least one real coordinate
+                    // phase A (every lane on its own data; only lane o's results are used)
+                    float x0 = x[0], x1 = x[1], t0 = 0.f, t1 = 0.f;
+                    const float m0 = cd_step_nb(b[0], inv[0], x0, L1, L2, t0);
+                    const float bl1 = fmaf(a[1][2 * o], m0, b[1]);
+                    const float m1 = cd_step_nb(bl1, inv[1], x1, L1, L2, t1);
+                    const float mult0 = __shfl_sync(0xffffffffu, m0, o);
+                    const float mult1 = __shfl_sync(0xffffffffu, m1, o);
+                    if (lane == o) {
+                        const bool e0 = (x0 == 0.f) && (x[0] != 0.f) && (t0 == 1.f);
+                        const bool e1 = (x1 == 0.f) && (x[1] != 0.f) && (t1 == 1.f);
+                        x[0] = x0; x[1] = x1;
+                        ev[0] = e0; ev[1] = e1;
+                        term[0] = e0 ? 0.f : t0;
+                        term[1] = e1 ? 0.f : t1;
+                    }
+                    // phase B, in coordinate order
+                    b[0] = fmaf(a[0][2 * o], mult0, b[0]);
+                    b[1] = fmaf(a[1][2 * o], mult0, b[1]);
+                    b[0] = fmaf(a[0][2 * o + 1], mult1, b[0]);
+                    b[1] = fmaf(a[1][2 * o + 1], mult1, b[1]);
+                }
+            }
+            // rebuild tol: the last clamp event in coordinate order (coordinate of slot c on this lane: 2 lane + c)
+            const uint32_t bal0 = __ballot_sync(0xffffffffu, ev[0]), bal1 = __ballot_sync(0xffffffffu, ev[1]);
+            const uint32_t any = bal0 | bal1;
+            int last = -1;
+            if (any) {
+                const int hl = 31 - __clz(any);
+                last = 2 * hl + (((bal1 >> hl) & 1u) ? 1 : 0);
+            }
+            float part = ((r0 > last) ? term[0] : 0.f) + ((r0 + 1 > last) ? term[1] : 0.f);
+            tol = warp_sum(part) + (last >= 0 ? 1.f : 0.f);
+        }
+        *reinterpret_cast<float2*>(X + col * KP + r0) = make_float2(x[0], x[1]);
+    }
+    sred[warp][r0] = in_range ? (double)x[0] : 0.0;
+    sred[warp][r0 + 1] = in_range ? (double)x[1] : 0.0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < KP; t += WARPS * 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) s += sred[w][t];
+        rowsum_part[blk * KP + t] = s;
+    }
+}
+
 // generic masked fallback for KP = 128: a_i, b, x in shared memory (one warp per CTA, padded rows)
 __global__ void __launch_bounds__(32)
 nnls_masked_big_kernel(const float* __restrict__ Bparts, int splits, float* __restrict__ X,
