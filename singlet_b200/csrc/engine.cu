@@ -948,7 +948,25 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
                     // (tail split -- full rounds on the two-column kernel, the remainder on the one-column-per-lane variant: 1.075 vs
                     //  1.075 ms on the 125,000-column shard and 1.69 vs 1.52 ms on the 250,000-column one. The tail costs one
                     //  column LATENCY, 3200 dependent coordinate steps x ~100 clk = 0.33 ms, whatever the lane holds)
-                    if (false) {}
+                    // Tail split. The columns make ncol / (768 per SM) rounds of the two-column grid and a round costs ~0.5 ms, but even a
+                    // handful of left-over columns costs one column LATENCY of this kernel (0.33 ms, above). The sub-warp kernel has a
+                    // shorter latency (blocks of four coordinates; ~0.1-0.15 ms per wave of 48 columns per SM), so a remainder of at
+                    // most two of its waves goes to it. Measured on the 125,000-column shard of a rank on 8 GPUs (remainder 11,336
+                    // columns = 1.6 waves): solver 1.080 -> 1.052 ms per iteration; a remainder within one wave saves ~0.15 ms.
+                    const int64_t cap = (int64_t)h->sm_count * 768;
+                    const int64_t full = ncol / cap * cap, rem = ncol - full;
+                    const bool no_split = getenv("SGL_NNLS_NO_TAIL_SPLIT") != nullptr;  // A/B tests
+                    if (full > 0 && rem > 0 && rem <= (int64_t)h->sm_count * 96 && !no_split) {
+                        static int occ2 = 0;
+                        if (!occ2 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, nnls_cols_kernel<32, 128, 2>, 128, 0) != cudaSuccess) occ2 = 1;
+                        nnls_cols_kernel<32, 128, 2><<<(unsigned)(h->sm_count * (occ2 > 0 ? occ2 : 1)), 128, 0, h->stream>>>(
+                            Bparts, splits, F_out, colptr, ncol, k, (float)L1, (float)L2, h->workctr.p, dbg_stats ? h->workctr.p + 2 : nullptr, full);
+                        constexpr int CPC = 4 * MaskedSubCfg<32>::G;  // columns per CTA of the sub-warp kernel; cap is a multiple of it
+                        const int64_t blk0 = full / CPC, blocks = (rem + CPC - 1) / CPC;
+                        SGL_TRY(h->part.ensure((size_t)(blk0 + blocks) * KPV));  // its row-sum partials are not used (rowsum pass below)
+                        nnls_masked_sub_kernel<32, 1><<<(unsigned)blocks, 128, 0, h->stream>>>(Bparts, splits, F_out, h->gram_f.p, F_in, colptr, nullptr,
+                                                                                              nullptr, ncol, k, (float)L1, (float)L2, h->part.p, nullptr, blk0);
+                    }
                     else if (ncol >= (int64_t)h->sm_count * 128 * 2) NNLS_LAUNCH(32, 128, 2)
                     else NNLS_LAUNCH(32, 32, 1)
                 } break;

@@ -103,9 +103,11 @@ nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
                  int splits, float* __restrict__ X,  // [ncol][KP] warm start in / solution out
                  const int64_t* __restrict__ colptr, int64_t ncol, int k, float L1, float L2,
                  unsigned long long* __restrict__ next_col,  // global work counter (zeroed by the host)
-                 unsigned long long* __restrict__ stats)     // optional: [0] += sweeps, [1] += columns solved
+                 unsigned long long* __restrict__ stats,     // optional: [0] += sweeps, [1] += columns solved
+                 int64_t col_end = -1)                       // solve columns [0, col_end) only (-1: all ncol; see the tail split)
 {
     __shared__ float sx[NCL * KP * NT];  // sx[(s * KP + i) * NT + tid]
+    if (col_end < 0) col_end = ncol;
 
     const int lane = threadIdx.x & 31;
     float2 b[NCL][KP / 2];  // right-hand sides as FP32 pairs (the rank-1 update runs on FFMA2)
@@ -153,7 +155,7 @@ nnls_cols_kernel(const float* __restrict__ Bparts,  // [splits][ncol][KP]
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (need) {
                     const int64_t c = (int64_t)base + __popc(mask & ((1u << lane) - 1u));
-                    if (c >= ncol) {
+                    if (c >= col_end) {
                         exhausted = true;
                         need = false;
                     } else if (colptr[c] != colptr[c + 1]) {  // empty columns are skipped (:340)

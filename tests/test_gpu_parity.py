@@ -92,6 +92,32 @@ def test_synth_device_matches_host():
         be.close()
 
 
+def test_plain_solver_tail_split(handle, oracle, monkeypatch):
+    """Column counts a little above a whole number of rounds of the thread-per-column solver's grid (768 columns per SM): the
+    full rounds are solved by that kernel and the short remainder by the sub-warp kernel (engine.cu, "tail split"). Both follow
+    the reference's coordinate order, so the split result equals the unsplit one to FP32 rounding and both match the oracle on a
+    sample of columns (reference src/singlet.cpp:229-250, 333-347)."""
+    import torch
+
+    from singlet_b200 import api, synth
+
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    m, n, k = 96, sms * 768 + sms * 60, 20  # remainder: 60 columns per SM (the split takes up to 96)
+    A = synth.synth_scipy(m, n, 0.2, seed=91)
+    w = synth.w_init(k, m, seed=92)
+    monkeypatch.delenv("SGL_NNLS_NO_TAIL_SPLIT", raising=False)
+    split = api.Rcpp_predict(A, w, 0.01, 0.0, 0)
+    monkeypatch.setenv("SGL_NNLS_NO_TAIL_SPLIT", "1")
+    whole = api.Rcpp_predict(A, w, 0.01, 0.0, 0)
+    monkeypatch.delenv("SGL_NNLS_NO_TAIL_SPLIT")
+    scale = np.abs(whole).max()
+    assert np.array_equal(split[:, :sms * 768], whole[:, :sms * 768])          # the full rounds are the same kernel
+    assert np.abs(split - whole).max() <= 2e-5 * scale                          # the remainder: another kernel, same algorithm
+    cols = np.r_[0:40, sms * 768 - 20:sms * 768 + 40, n - 40:n]
+    ref = oracle.predict(A[:, cols].tocsc(), w, np.zeros((k, len(cols))), 0.01, 0.0)
+    assert np.abs(split[:, cols] - ref).max() <= 2e-4 * np.abs(ref).max()
+
+
 @pytest.fixture
 def fp32_operands(handle):
     """Run a test with FP32 gather operands (sgl_set_precision); the default 16-bit staging is restored afterwards."""
