@@ -274,6 +274,39 @@ static inline uint64_t hash_block(const int32_t* si, const double* sx, int64_t l
     }
     return splitmix64(h0 ^ splitmix64(h1 ^ splitmix64(h2 ^ splitmix64(h3 ^ (uint64_t)len))));
 }
+// hash_block and the record packing of the upload in ONE pass over the piece (the piece, 6 MB of i / x, does not fit the
+// core's L2: hashing first and packing afterwards read it from memory twice). Returns exactly hash_block(si, sx, len).
+static inline uint64_t hash_and_pack(const int32_t* si, const double* sx, int64_t len, uint2* buf) {
+    const uint64_t K = 0x9E3779B97F4A7C15ull;
+    uint64_t h0 = 0x243F6A8885A308D3ull, h1 = 0x13198A2E03707344ull, h2 = 0xA4093822299F31D0ull, h3 = 0x082EFA98EC4E6C89ull;
+    auto rec = [](int32_t row, double v) {
+        const float f = (float)v;
+        uint32_t bits;
+        std::memcpy(&bits, &f, 4);
+        return make_uint2((uint32_t)row, bits);
+    };
+    int64_t t = 0;
+    for (; t + 4 <= len; t += 4) {
+        uint64_t x[4], iw[2];
+        std::memcpy(x, sx + t, 32);
+        std::memcpy(iw, si + t, 16);
+        h0 = (h0 ^ x[0]) * K; h0 ^= h0 >> 29;
+        h1 = (h1 ^ x[1]) * K; h1 ^= h1 >> 29;
+        h2 = (h2 ^ x[2] ^ iw[0]) * K; h2 ^= h2 >> 29;
+        h3 = (h3 ^ x[3] ^ (iw[1] << 1)) * K; h3 ^= h3 >> 29;
+        buf[t] = rec(si[t], sx[t]);
+        buf[t + 1] = rec(si[t + 1], sx[t + 1]);
+        buf[t + 2] = rec(si[t + 2], sx[t + 2]);
+        buf[t + 3] = rec(si[t + 3], sx[t + 3]);
+    }
+    for (; t < len; ++t) {
+        uint64_t x;
+        std::memcpy(&x, sx + t, 8);
+        h0 = (h0 ^ x ^ ((uint64_t)(uint32_t)si[t] << 7)) * K; h0 ^= h0 >> 29;
+        buf[t] = rec(si[t], sx[t]);
+    }
+    return splitmix64(h0 ^ splitmix64(h1 ^ splitmix64(h2 ^ splitmix64(h3 ^ (uint64_t)len))));
+}
 static inline uint64_t hash_piece_mix(uint64_t hb, int chunk, int64_t piece) {
     return splitmix64(hb + 0x9E3779B97F4A7C15ull * (((uint64_t)chunk << 40) ^ (uint64_t)piece ^ 0x5851F42D4C957F2Dull));
 }
@@ -440,13 +473,7 @@ static int matrix_upload(sgl_handle* h, const sgl_csc* chunks, int n_chunks, sgl
                 uint2* buf = h->stage[wid][use];
                 const int32_t* si = c.i + cbase + o;
                 const double* sx = c.x + cbase + o;
-                worker_hash[(size_t)wid] ^= hash_piece_mix(hash_block(si, sx, len), q, pc);
-                for (int64_t t = 0; t < len; ++t) {
-                    const float v = (float)sx[t];
-                    uint32_t bits;
-                    std::memcpy(&bits, &v, 4);
-                    buf[t] = make_uint2((uint32_t)si[t], bits);
-                }
+                worker_hash[(size_t)wid] ^= hash_piece_mix(hash_and_pack(si, sx, len, buf), q, pc);
                 if (cudaMemcpyAsync(dst_dev + o, buf, sizeof(uint2) * (size_t)len, cudaMemcpyHostToDevice, h->stage_stream[wid]) != cudaSuccess)
                     worker_rc[(size_t)wid] = 1;
                 cudaEventRecord(h->stage_ev[wid][use], h->stage_stream[wid]);
@@ -1487,7 +1514,9 @@ static int transpose_on_device(sgl_handle* h, const sgl_matrix* X, sgl_matrix** 
 // cached in the same slot under a fingerprint derived from A's
 static int cached_At(sgl_handle* h, const sgl_csc* At_, int nAt, sgl_matrix* A, sgl_matrix** out) {
     if (At_ && nAt > 0) return cached_upload(h, At_, nAt, &h->cAt, &h->cmAt, out);
-    const uint64_t fp = splitmix64(A->fingerprint ^ 0x7472616e73706f73ull);
+    // keyed by A's CONTENT hash as well: an in-place edit that the sampled fingerprint does not see re-uploads A (cached_upload)
+    // and must rebuild its transpose too (found by tests/test_gpu_parity.py::test_upload_cache_sees_in_place_edits)
+    const uint64_t fp = splitmix64(A->fingerprint ^ splitmix64(A->content_hash) ^ 0x7472616e73706f73ull);
     if (h->cache && h->cAt && h->cAt->fingerprint == fp) {
         *out = h->cAt;
         return SGL_OK;

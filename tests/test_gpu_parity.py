@@ -92,6 +92,36 @@ def test_synth_device_matches_host():
         be.close()
 
 
+def test_upload_cache_sees_in_place_edits(oracle):
+    """The upload cache (one handle per R session keeps A / At resident between calls) is keyed by a hash of EVERY byte of the
+    host p / i / x: a repeated call on the unchanged matrix reuses the device copy, an in-place edit of ONE value that the cheap
+    fingerprint does not sample (the R idiom `A@x[j] <- v`) re-uploads it."""
+    from singlet_b200 import api, synth
+
+    m, n, k = 400, 9000, 6
+    A = synth.synth_scipy(m, n, 0.05, seed=31)
+    assert A.nnz > 3 * 4096  # the fingerprint samples every (nnz / 4096)-th value: entry 1 is not one of them
+    w0 = synth.w_init(k, m, seed=32)
+    h = api.Handle(0)
+    try:
+        first = api.c_nmf(A, None, 0.0, 4, False, 0.01, 0.01, 0, 0, 0, w0, h)
+        again = api.c_nmf(A, None, 0.0, 4, False, 0.01, 0.01, 0, 0, 0, w0, h)
+        assert np.array_equal(first["h"], again["h"]) and np.array_equal(first["w"], again["w"])
+        col = int(np.searchsorted(A.indptr, 1, side="right") - 1)  # the column that holds entry 1
+        A.data[1] *= 50.0
+        edited = api.c_nmf(A, None, 0.0, 4, False, 0.01, 0.01, 0, 0, 0, w0, h)
+        assert not np.array_equal(first["h"][:, col], edited["h"][:, col])
+        fresh = api.Handle(0)
+        try:
+            fresh.set_cache(False)
+            ref = api.c_nmf(A, None, 0.0, 4, False, 0.01, 0.01, 0, 0, 0, w0, fresh)
+        finally:
+            fresh.close()
+        assert np.array_equal(edited["h"], ref["h"]) and np.array_equal(edited["w"], ref["w"])
+    finally:
+        h.close()
+
+
 def test_plain_solver_tail_split(handle, oracle, monkeypatch):
     """Column counts a little above a whole number of rounds of the thread-per-column solver's grid (768 columns per SM): the
     full rounds are solved by that kernel and the short remainder by the sub-warp kernel (engine.cu, "tail split"). Both follow
