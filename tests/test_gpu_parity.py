@@ -118,6 +118,72 @@ def test_upload_cache_sees_in_place_edits(oracle):
         finally:
             fresh.close()
         assert np.array_equal(edited["h"], ref["h"]) and np.array_equal(edited["w"], ref["w"])
+        # the same for the masked path (the masks hold copies of the values) and for the batched rank search (its workers
+        # share the cached matrices)
+        args = (0.0, 3, False, 0.01, 0.0, 0, w0, 55, 12, 10.0, 2)
+        before = api.c_ard_nmf(A, None, *args, h)
+        A.data[1] /= 50.0
+        after = api.c_ard_nmf(A, None, *args, h)
+        assert not np.array_equal(before["test_mse"], after["test_mse"]) or not np.array_equal(before["h"], after["h"])
+        batch = api.c_ard_nmf_batch(A, None, 0.0, 3, 0.01, 0.0, 0, [w0, w0[:4]], [55, 56], 12, 10.0, 2, handle=h)
+        fresh = api.Handle(0)
+        try:
+            fresh.set_cache(False)
+            ref_m = api.c_ard_nmf(A, None, *args, fresh)
+            ref_b = api.c_ard_nmf(A, None, 0.0, 3, False, 0.01, 0.0, 0, w0[:4], 56, 12, 10.0, 2, fresh)
+        finally:
+            fresh.close()
+        for key in ("w", "d", "h", "test_mse"):
+            assert np.array_equal(after[key], ref_m[key]) and np.array_equal(batch[0][key], ref_m[key]) and np.array_equal(batch[1][key], ref_b[key]), key
+    finally:
+        h.close()
+
+
+def test_handle_state_does_not_leak_between_calls():
+    """One handle per R session serves every call: cached uploads, transposes, masks (refilled in place when the seed changes),
+    tile indices per padded rank and operand format, grow-only factor buffers, the FP16 shadow. A call must give the same
+    result whatever ran before it on the handle."""
+    from singlet_b200 import api, synth
+
+    A1 = synth.synth_scipy(700, 500, 0.08, seed=61)
+    A2 = synth.synth_scipy(350, 900, 0.05, seed=62)
+    h = api.Handle(0)
+
+    def plain(A, k):
+        return api.c_nmf(A, None, 0.0, 4, False, 0.01, 0.01, 0, 0, 0, synth.w_init(k, A.shape[0], seed=k), h)
+
+    def masked(A, k, seed):
+        return api.c_ard_nmf(A, None, 0.0, 4, False, 0.01, 0.0, 0, synth.w_init(k, A.shape[0], seed=k), seed, 15, 10.0, 2, h)
+
+    def same(a, b, keys=("w", "d", "h")):
+        return all(np.array_equal(a[q], b[q]) for q in keys)
+
+    try:
+        base = {("p", 1, 5): plain(A1, 5), ("p", 1, 20): plain(A1, 20), ("p", 1, 40): plain(A1, 40), ("p", 2, 9): plain(A2, 9)}
+        m1 = masked(A1, 20, 77)
+        m2 = masked(A1, 20, 78)       # another seed: the mask is refilled in place
+        assert not np.array_equal(m1["test_mse"], m2["test_mse"])
+        assert same(masked(A1, 20, 77), m1, ("w", "d", "h", "test_mse"))
+        m3 = masked(A2, 6, 77)        # another matrix: upload, transpose and masks are replaced
+        assert same(plain(A1, 5), base[("p", 1, 5)])
+        assert same(masked(A2, 6, 77), m3, ("w", "d", "h", "test_mse"))
+        assert same(plain(A1, 40), base[("p", 1, 40)]) and same(plain(A2, 9), base[("p", 2, 9)]) and same(plain(A1, 20), base[("p", 1, 20)])
+        # operand precision switched back and forth on the same handle (different stream formats, the FP16 shadow, the
+        # single-pass Gram correction)
+        h.set_precision("mixed16_always")
+        p16 = plain(A1, 40)
+        q16 = masked(A1, 20, 77)
+        h.set_precision("fp32")
+        assert same(plain(A1, 40), base[("p", 1, 40)])
+        h.set_precision("mixed16_always")
+        assert same(plain(A1, 40), p16) and same(masked(A1, 20, 77), q16, ("w", "d", "h", "test_mse"))
+        h.set_precision("mixed16")
+        assert same(masked(A1, 20, 77), m1, ("w", "d", "h", "test_mse"))
+        # projection with a model of another rank in between
+        pr = api.c_project_model(A1, base[("p", 1, 5)]["w"], 0.01, 0.0, 0, h)
+        plain(A2, 9)
+        pr2 = api.c_project_model(A1, base[("p", 1, 5)]["w"], 0.01, 0.0, 0, h)
+        assert np.array_equal(pr["h"], pr2["h"]) and np.array_equal(pr["d"], pr2["d"])
     finally:
         h.close()
 
