@@ -265,8 +265,8 @@ Rcpp::List c_ard_nmf_batch(Rcpp::SparseMatrix& A, Rcpp::SparseMatrix& At, const 
 
 // ---- several GPUs from the one R process ------------------------------------------------------------------
 // The chunk-list entry points are what shards: with options(singlet.gpus = G > 1) the two *_sparse_list functions above are
-// replaced by these bodies. `At_` is accepted and ignored (the transposed blocks are built on the devices), so the
-// "distributed transpose" of R/cross_validate_nmf.R:37-50 can be dropped by a maintainer but does no harm.
+// replaced by these bodies. The plain fit ignores `At_` (the transposed blocks are built on the devices), so for run_nmf-style
+// calls the "distributed transpose" of R/cross_validate_nmf.R:37-50 can be dropped; the masked fit uses it.
 namespace {
 sgl_multi* multi(int n_gpus) {  // one multi-GPU context per R session
     static sgl_multi* mg = nullptr;
@@ -292,11 +292,12 @@ Rcpp::List c_nmf_sparse_list_multi(int n_gpus, Rcpp::List A_, const double tol, 
     return Rcpp::List::create(Rcpp::Named("w") = w, Rcpp::Named("d") = d, Rcpp::Named("h") = h);
 }
 
-Rcpp::List c_ard_nmf_sparse_list_multi(int n_gpus, Rcpp::List A_, const double tol, const uint16_t maxit, const bool verbose,
+// (the masked fit shards the genes for the W update too, so it takes the reference's "distributed transpose" list At_ as it is)
+Rcpp::List c_ard_nmf_sparse_list_multi(int n_gpus, Rcpp::List A_, Rcpp::List At_, const double tol, const uint16_t maxit, const bool verbose,
                                        const double L1, const double L2, Eigen::MatrixXd w, const uint64_t rng_seed,
                                        const uint64_t inv_density, const double overfit_threshold, const uint16_t trace_test_mse) {
-    std::vector<Rcpp::SparseMatrix> A = as_list(A_);
-    std::vector<sgl_csc> a = views(A);
+    std::vector<Rcpp::SparseMatrix> A = as_list(A_), At = as_list(At_);
+    std::vector<sgl_csc> a = views(A), at = views(At);
     const int k = (int)w.rows();
     int64_t n = 0;
     for (auto& c : a) n += c.ncol;
@@ -308,7 +309,7 @@ Rcpp::List c_ard_nmf_sparse_list_multi(int n_gpus, Rcpp::List A_, const double t
     sgl_trace tr{mse.data(), it.data(), ft.data(), so.data(), cap, 0};
     Progress p{verbose, true};
     sgl_callbacks cb = callbacks(p);
-    check(sgl_multi_ard_nmf(multi(n_gpus), a.data(), (int)a.size(), nullptr, 0, tol, maxit, L1, L2, k, w.data(), d.data(), h.data(),
+    check(sgl_multi_ard_nmf(multi(n_gpus), a.data(), (int)a.size(), at.data(), (int)at.size(), tol, maxit, L1, L2, k, w.data(), d.data(), h.data(),
                             rng_seed, inv_density, overfit_threshold, trace_test_mse, &tr, &cb));
     return Rcpp::List::create(Rcpp::Named("w") = w, Rcpp::Named("d") = d, Rcpp::Named("h") = h,
                               Rcpp::Named("test_mse") = Rcpp::NumericVector(mse.begin(), mse.begin() + tr.length),
