@@ -415,6 +415,30 @@ def test_tensor_core_gram_correction_matches_fp32_and_oracle(handle, oracle, mon
         assert np.allclose(one["test_mse"], two["test_mse"], rtol=2e-5)
 
 
+@pytest.mark.parametrize("inv_density", [2, 300])
+def test_tensor_core_gram_correction_list_lengths(handle, oracle, monkeypatch, inv_density):
+    """Held-out lists far from the usual 5 %: half of every column (450 entries: many 16-entry blocks and a partial one) and
+    1 / 300 (most columns hold 0 - 6 entries: empty lists, lists shorter than the ring is deep)."""
+    from singlet_b200 import api, synth
+
+    m, n, k = 900, 330, 24
+    A, At = _mk(m, n, 0.1, seed=5, empty_cols=(7,))
+    w0 = synth.w_init(k, m, seed=6)
+    args = (A, At, 0.0, 5, False, 0.01, 0.0, 0, w0, 31, inv_density, 10.0, 2)
+    monkeypatch.delenv("SGL_GRAMCORR", raising=False)
+    mma = api.c_ard_nmf(*args)
+    monkeypatch.setenv("SGL_GRAMCORR", "ffma")
+    ffma = api.c_ard_nmf(*args)
+    monkeypatch.delenv("SGL_GRAMCORR")
+    ref = oracle.ard_nmf(A, At, w0, 31, inv_density, tol=0.0, maxit=5, L1=0.01, L2=0.0, overfit_threshold=10.0, trace_test_mse=2)
+    for dev in (mma, ffma):
+        assert list(dev["iter"]) == list(ref["iter"])
+        assert np.allclose(dev["test_mse"], ref["test_mse"], rtol=MSE_RTOL)
+        perm = match_factors(ref["w"], dev["w"])
+        assert min_factor_cor(ref["w"], dev["w"], perm) >= COR_MIN and min_factor_cor(ref["h"], dev["h"], perm) >= COR_MIN
+    assert np.allclose(mma["test_mse"], ffma["test_mse"], rtol=5e-5)
+
+
 def test_ard_overfit_break(handle, oracle):
     """The early `break` on score_overfit > threshold leaves iter_ un-incremented (App. A-13)."""
     from singlet_b200 import api, synth
