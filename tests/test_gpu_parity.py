@@ -188,6 +188,28 @@ def test_handle_state_does_not_leak_between_calls():
         h.close()
 
 
+def test_large_factor_download_paths_agree(monkeypatch):
+    """A factor of >= 4 M entries comes back through the upload workers' pinned staging buffers (FP32 over PCIe, widened by
+    host threads); with a single worker the library takes the plain path (one device-side conversion + one copy). Same bytes."""
+    from singlet_b200 import api, synth
+
+    A = synth.synth_scipy(1500, 250000, 0.01, seed=5)
+    w0 = synth.w_init(20, 1500, seed=6)   # padded rank 32 != 20: the staged rows carry padding that must be dropped
+    monkeypatch.setenv("SGL_UPLOAD_THREADS", "1")
+    h1 = api.Handle(0)
+    try:
+        a = api.c_nmf(A, None, 0.0, 2, False, 0.01, 0.01, 0, 0, 0, w0, h1)
+    finally:
+        h1.close()
+    monkeypatch.delenv("SGL_UPLOAD_THREADS")
+    h2 = api.Handle(0)
+    try:
+        b = api.c_nmf(A, None, 0.0, 2, False, 0.01, 0.01, 0, 0, 0, w0, h2)
+    finally:
+        h2.close()
+    assert a["h"].shape == (20, 250000) and np.array_equal(a["h"], b["h"]) and np.array_equal(a["w"], b["w"]) and np.array_equal(a["d"], b["d"])
+
+
 def test_plain_solver_tail_split(handle, oracle, monkeypatch):
     """Column counts a little above a whole number of rounds of the thread-per-column solver's grid (768 columns per SM): the
     full rounds are solved by that kernel and the short remainder by the sub-warp kernel (engine.cu, "tail split"). Both follow
