@@ -1443,7 +1443,8 @@ static int cached_upload(sgl_handle* h, const sgl_csc* chunks, int n, sgl_matrix
 // X^T on the device (kernels in misc.cuh). One pass over the records per 57,856 rows of X (the per-row
 // counters of a CTA live in shared memory): a single pass for A (rows = genes), several for matrices with more rows.
 static int transpose_on_device(sgl_handle* h, const sgl_matrix* X, sgl_matrix** out) {
-    const int64_t max_rows = (227 * 1024 - 1024) / 4;
+    int64_t max_rows = (227 * 1024 - 1024) / 4;
+    if (const char* ev = getenv("SGL_TRANSPOSE_ROWS")) max_rows = atoll(ev) > 0 && atoll(ev) < max_rows ? atoll(ev) : max_rows;  // experiments
     if (X->ncol > 0x7fffffffLL) return fail(SGL_EINVAL, "device transpose: too many columns for int32 row indices of the transpose");
     SGL_TRY(set_device(h));
     sgl_matrix* t = new sgl_matrix();
