@@ -274,3 +274,23 @@ def test_run_nmf_host_logic(monkeypatch):
     api.set_seed(99)
     api.run_nmf(A, 4, maxit=2, verbose=False, device_transpose=False)
     assert got["At"] is not None and (got["At"] != A.T.tocsc()).nnz == 0
+
+
+def test_sass_of_the_shipped_library():
+    """The shipped library is sm_100a code and carries the instructions DESIGN.md claims (B200_PROFILING.md, "SASS mnemonics"):
+    bulk TMA copies with mbarrier synchronisation for the factor tiles of the sparse product (UBLKCP, SYNCS), cp.async rings
+    (LDGSTS), the mixed-precision FMA of the 16-bit-operand product (FHFMA), and the tensor-core Gram corrections of the masked
+    solver (HMMA.16816 on BF16 and FP16 operands fed by ldmatrix = LDSM)."""
+    import shutil
+    import subprocess
+
+    from singlet_b200 import _lib
+
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run([tool, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"arch = (sm_\w+)", sass))
+    assert archs == {"sm_100a"}, archs
+    for mnemonic in ("UBLKCP", "SYNCS", "LDGSTS", "FHFMA", "LDSM", "HMMA.16816.F32.BF16", "HMMA.16816.F32 "):
+        assert mnemonic in sass, mnemonic
