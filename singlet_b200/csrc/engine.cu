@@ -960,13 +960,13 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
                 NNLS_CASE(4) NNLS_CASE(8) NNLS_CASE(16) NNLS_CASE(64)
                 case 32: {
                     // (three columns per lane -- 168 registers, 1152 columns in flight per SM -- measured slower: 5.96 vs 4.94 ms
-                    //  for 10^6 columns; profiles/r2_nnls.md)
+                    //  for 10^6 columns; profiles/r2_summary.md section 3)
                     // (a 128-register build that keeps 4 CTAs per SM resident, so that one eighth of the headline config's cells
                     //  -- 125,000 columns -- makes ONE round of the grid, and a sweep that skips warp-empty slots were measured too:
-                    //  no gain / slower; the kernel is FP32-pipe bound either way -- profiles/r2_nnls.md)
+                    //  no gain / slower; the kernel is FP32-pipe bound either way -- profiles/r2_summary.md section 3)
                     // (tried for the 125,000-column case of a rank on 8 GPUs, 1.1 rounds of the grid: a 128-register build with 4 CTAs
                     //  or 16 one-warp CTAs per SM so that ONE round suffices, three columns per lane, and a sweep that skips warp-empty
-                    //  slots. None beat 0.83 ms: the 128-register code is ~45 % slower per column -- profiles/r2_nnls.md)
+                    //  slots. None beat 0.83 ms: the 128-register code is ~45 % slower per column -- profiles/r2_summary.md section 3)
                     // (two CTAs per SM, i.e. two balanced rounds of 8 warps instead of 1.1 rounds of 12: 1.06 vs 1.05 ms of solver
                     //  per iteration on that shard, and slower on the 250,000- and 500,000-column shards; handing the last 0.1
                     //  round to the sub-warp kernel would cost 0.17 ms for 11,400 columns against the 0.33 ms it replaces)

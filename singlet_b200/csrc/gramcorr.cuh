@@ -2,7 +2,7 @@
 //     G_M(c) = sum over the held-out rows r of column c of f_r f_r^T        (reference src/singlet.cpp:460-461)
 // so that the solver can use a_c = G - G_M(c) (:462). k^2 multiply-adds per held-out entry: at cross-validation sizes this
 // is 40 % of the masked solver's instructions, on a large matrix (30k x 100k, k = 32: 3e8 held-out entries per iteration)
-// it is 94 % of the whole ALS iteration when done with FP32 FMAs (profiles/r2_masked.md).
+// it is 94 % of the whole ALS iteration when done with FP32 FMAs (profiles/r2_summary.md section 4).
 //
 // One warp = one column. The operand is the OTHER factor F (k x rows, FP32). It is split once per half-iteration into two
 // BF16 planes, hi = bf16(F) and mid = bf16(F - hi): 16 mantissa bits together. The held-out rows are gathered 16 at a time
@@ -13,7 +13,7 @@
 // i.e. two tensor passes instead of three because the two cross terms are transposes of each other; the transpose is done
 // once per column through the (then idle) ring. Error of G_M: ~2^-17 relative per product, averaging down over the list
 // -- the same order as the FP32 accumulation error of the FFMA path (tests/test_gpu_parity.py compares both paths).
-// Measured (scripts/microbench, profiles/r2_microbench.md): 1.14 clk per (column, held-out row) per SM and pass against
+// Measured (scripts/microbench, profiles/r2_microbench.txt): 1.14 clk per (column, held-out row) per SM and pass against
 // ~8 clk at the FP32 FMA peak. tcgen05.mma was considered and not used: its smallest tile is M = 64 x N = 8 per CTA with the
 // operands described as whole shared-memory tiles; here every column has its OWN 32 x 32 output and its own gathered row list,
 // so four columns would have to share one 128 x 128 accumulator of which only the diagonal blocks are wanted (75 % wasted
@@ -139,7 +139,7 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
     // of whole 32-byte sectors and lands in shared memory as whole conflict-free lines. (One lane per 16 bytes with the two
     // planes 2 * KP bytes apart, as first written, fetched every sector twice: 264 B per entry over the L2 crossbar; a padded
     // 144-byte row split the shared-memory side of each request into ~10 wavefronts and still moved 200 B per entry --
-    // profiles/r2_masked.md.) The row index of entry e of the block is held by lane e.
+    // profiles/r2_summary.md section 4.) The row index of entry e of the block is held by lane e.
     constexpr int CPE = C::CPE, EPI = 32 / CPE, NI = C::BLK / EPI;
     auto load_idx = [&](int blk) -> uint32_t {
         const int t = blk * C::BLK + (lane & 15);
@@ -166,7 +166,7 @@ gram_corr_mma_kernel(const uint16_t* __restrict__ pairs, const int64_t* __restri
     // before the copy that needs them is issued. The loop is unrolled by U = 2 with one index register per residue: rotating
     // two registers made the compiler wait for the younger load at the rotation itself (55 % of the stall samples), one
     // block of distance left 17 % of the samples on the shuffle that consumes the index, two blocks 25 % of fewer samples
-    // (1.15 -> 1.05 ms), and four blocks (U = 4) was slower again (profiles/r2_masked.md).
+    // (1.15 -> 1.05 ms), and four blocks (U = 4) was slower again (profiles/r2_summary.md section 4).
     constexpr int U = 2;
     static_assert(C::STAGES % U == 0, "block b and block b + STAGES share an index register");
     uint32_t idx_r[U];

@@ -412,7 +412,7 @@ mask_records_kernel(MaskGen gen, int64_t ncol, const int64_t* __restrict__ colpt
 // LPE = KP / 4 lanes cooperate on one entry: each reads 16 bytes of the gene's W row, so a group reads one contiguous
 // 4 * KP-byte piece (a whole 128-byte line at KP = 32) and the warp covers 32 / LPE entries per step; the partial dot
 // products are folded with log2(LPE) shuffles. (One entry per lane -- every lane walking a whole row of its own -- kept the
-// L1 at 98 % of its wavefront rate: 2.17 ms for 7.5e7 held-out entries at k = 32, profiles/r2_masked.md.)
+// L1 at 98 % of its wavefront rate: 2.17 ms for 7.5e7 held-out entries at k = 32, profiles/r2_summary.md section 4.)
 // Writes per-column losses; the caller reduces them in fixed order.
 // ----------------------------------------------------------------------------------------------
 template <int KP>

@@ -9,7 +9,7 @@
 // KP-float row of F (128 B at KP = 32) against 8 B of HBM stream, and the crossbar moves 128 B/clk/SM. A 16-bit
 // operand halves the gather and the TMA tile fill, and the tile holds twice the rows, so the padding of the
 // per-(column, tile) sub-ranges halves too. Keeping v in FP32 needs an HADD2.F32 conversion per gathered half; that
-// instruction only issues on the fmaheavy pipe at half rate and became the bound (measured: profiles/r2_spmm.md),
+// instruction only issues on the fmaheavy pipe at half rate and became the bound (measured: profiles/r2_summary.md section 2),
 // hence the FP16 value and the mixed-precision FMA.
 //
 // Layout differences from spmm.cuh (same "warp stream" idea, one contiguous record array per column group):
@@ -24,7 +24,7 @@
 //   * KP = 32: a row is 64 B, so an 8-lane LDS.128 phase covers TWO rows; they are conflict-free only when they sit
 //     in opposite halves of the 128-byte bank line (row parity). The records of a sub-range are therefore stored
 //     with even and odd rows alternating (the surplus parity at the end), which makes all phases but the surplus
-//     conflict-free (microbench: scripts/microbench, profiles/r2_microbench.md).
+//     conflict-free (microbench: scripts/microbench, profiles/r2_microbench.txt).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -356,7 +356,7 @@ spmm_h16_kernel(const uint32_t* __restrict__ stream,  // warp streams of 4-byte 
         return w;
     };
     // (reading the records one block ahead and handing them over in registers was measured SLOWER: the four extra moves
-    //  per block cost more issue slots than the hidden LDS latency gives back -- profiles/r2_spmm.md)
+    //  per block cost more issue slots than the hidden LDS latency gives back -- profiles/r2_summary.md section 2)
     uint32_t phase0 = 0, phase1 = 0;
     for (int t = t_begin; t < t_end; ++t) {
         const int s = (t - t_begin) & 1;
