@@ -596,6 +596,7 @@ def e2e_leg_sharded(be, comm, cfg, steps, A_dev, rank, world):
     arr, na, keep = _lib.chunks_to_c([A])
     hA = C.c_void_p()
     _lib.check(lib.sgl_matrix_upload(be._h, arr, na, C.byref(hA)))
+    sec_upload = time.perf_counter() - t0
     _lib.check(lib.sgl_nmf_rank(comm._c, hA, None, n, 0.0, steps, L1, L1, L2, L2, k, w.ctypes.data, d.ctypes.data, h_loc.ctypes.data,
                                 C.addressof(iters), None, None))
     sec_local = time.perf_counter() - t0
@@ -608,7 +609,8 @@ def e2e_leg_sharded(be, comm, cfg, steps, A_dev, rank, world):
     sec = float(dt[0])
     assert iters.value == steps
     return {"value": steps / sec, "unit": "iterations/s", "h2d_bytes_per_step": float(h2d[0]) / steps, "d2h_bytes_per_step": d2h / steps,
-            "seconds_total": sec, "iterations": steps, "call": "sgl_matrix_upload + sgl_nmf_rank per rank (include/singlet_cuda.h)",
+            "seconds_total": sec, "iterations": steps, "rank0_seconds": {"upload": sec_upload, "fit_and_download": sec_local - sec_upload},
+            "call": "sgl_matrix_upload + sgl_nmf_rank per rank (include/singlet_cuda.h)",
             "note": "every rank uploads its host dgCMatrix cell shard (FP64), transposes it on the device, runs K iterations and downloads "
                     "w, d and its own block of h; max over ranks"}
 

@@ -467,11 +467,23 @@ static int nmf_rank(sgl_comm* c, const sgl_matrix* A_loc, const sgl_matrix* At_l
                     double L1_h, double L2_w, double L2_h, int k, double* w, double* d, double* h_local, int32_t* iters_out, double* tol_out,
                     const sgl_callbacks* cb, RankShared* shared) {
     sgl_fit* f = nullptr;
+    // SGL_TIMING=1: wall-clock phases of this rank on stderr (developer aid, like the single-GPU entry points)
+    const bool timing = getenv("SGL_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(c->stream);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sgl timing] rank %d %-34s %9.3f ms\n", c->rank, what, std::chrono::duration<double, std::milli>(t1 - t_last).count());
+        t_last = t1;
+    };
     SGL_TRY(sgl_fit_create(c, A_loc, At_loc, n_total, k, w, 0, 0, 0, &f));
+    mark("fit_create (transpose, gene counts)");
     double tol_ = 1;
     uint16_t iter_ = 0;
     int rc = SGL_OK;
     for (; iter_ < maxit && tol_ > tol; ++iter_) {  // src/singlet.cpp:647
+        if (iter_ == 1) mark("first iteration (+ tiles)");
         int stop = 0;
         if (cb && cb->poll_interrupt && cb->poll_interrupt(cb->user)) stop = 1;
         if (shared && shared->stop.load()) stop = 1;
@@ -483,11 +495,13 @@ static int nmf_rank(sgl_comm* c, const sgl_matrix* A_loc, const sgl_matrix* At_l
         }
         if (stop) { rc = fail(SGL_EINTERRUPT, "interrupted"); break; }
     }
+    mark("other iterations");
     if (rc == SGL_OK) {
         if (iters_out) *iters_out = iter_;
         if (tol_out) *tol_out = tol_;
         rc = sgl_fit_download(f, w, d, h_local);
     }
+    mark("download");
     fit_release(f);
     return rc;
 }
