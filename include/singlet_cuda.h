@@ -227,10 +227,23 @@ int sgl_dev_rhs(sgl_handle* h, const sgl_matrix* X, const float* F_in, int k, fl
 int sgl_dev_solve(sgl_handle* h, const float* B, const int64_t* colptr_like, int64_t ncol, float* F_out, int k,
                   const double* gram, double L1, double L2, double* rowsum);
 
+/* sgl_dev_update in two calls on the handle's own right-hand-side scratch, so that a driver can enqueue the product
+ * (which only reads F_in) ahead of time: sgl_dev_update_rhs leaves b = F_in . X in the handle and returns a ticket;
+ * sgl_dev_update_solve runs the NNLS of sgl_dev_update on it and fails with SGL_EINVAL when another product on this
+ * handle has overwritten the scratch since (compare the ticket with sgl_dev_rhs_epoch first and redo the product). */
+int sgl_dev_update_rhs(sgl_handle* h, const sgl_matrix* X, const float* F_in, int k, uint64_t* ticket_out);
+uint64_t sgl_dev_rhs_epoch(const sgl_handle* h);
+int sgl_dev_update_solve(sgl_handle* h, const sgl_matrix* X, uint64_t ticket, float* F_out, int k, const double* gram,
+                         double L1, double L2, double* rowsum);
+
 /* scale (src/singlet.cpp:219-225): F[c][f] /= d[f]; d is double[KP] on the device (already
  * all-reduced and with the 1e-15 added -- see sgl_dev_finish_d). */
 int sgl_dev_finish_d(sgl_handle* h, int k, double* d_inout);
 int sgl_dev_scale(sgl_handle* h, float* F, int k, int64_t cols, const double* d);
+/* sgl_dev_finish_d, and in the same launch the Gram of the factor BEFORE scaling (sgl_dev_gram without jitter, summed
+ * over the ranks) becomes the Gram of the scaled factor: gram[i][j] / (d[i] d[j]), 1e-15 added to the diagonal
+ * (src/singlet.cpp:206). With it the row sums of `scale` and the partial Grams travel in ONE all-reduce. */
+int sgl_dev_finish_d_rescale_gram(sgl_handle* h, int k, double* d_inout, double* gram_inout);
 
 /* cor (src/singlet.cpp:184-197): the five running sums over the given columns -> sums[5] (double,
  * device): sum x, sum y, sum xy, sum x^2, sum y^2. sgl_cor_from_sums finishes on the host. */
@@ -302,6 +315,10 @@ int sgl_fit_create(sgl_comm* c, const sgl_matrix* A_loc, const sgl_matrix* At_lo
 /* one trip of src/singlet.cpp:648-659 (:1108-1114 when masked), collectives included; tol_out = 1 - cor(w, w_prev).
  * stop_flag (optional, in/out): set to 1 on any rank to make EVERY rank leave with 1 (agreed through the all-reduce). */
 int sgl_fit_iterate(sgl_fit* f, double L1_w, double L1_h, double L2_w, double L2_h, double* tol_out, int* stop_flag);
+/* Plain fits enqueue the part of the NEXT iteration that only reads W (its Gram, the H-update product) before the host waits
+ * for tol, so the device does not idle across the host round trip; results are unchanged. on = 0 before the last iteration
+ * of a fit avoids one wasted product (sgl_nmf_rank does). Default: on. */
+int sgl_fit_set_lookahead(sgl_fit* f, int on);
 int sgl_fit_test_mse(sgl_fit* f, double* out);                            /* mse_test, all-reduced */
 int sgl_fit_download(sgl_fit* f, double* w, double* d, double* h_local);  /* k x m, k, k x n_loc; any may be NULL */
 int sgl_fit_shard(const sgl_fit* f, int64_t* c0, int64_t* c1, int64_t* g0, int64_t* g1);

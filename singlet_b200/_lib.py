@@ -95,7 +95,11 @@ SYMBOLS = [
     ("sgl_dev_update", _i32, [_vp, _vp, _vp, _vp, _i32, _vp, _dbl, _dbl, _vp]),
     ("sgl_dev_rhs", _i32, [_vp, _vp, _vp, _i32, _vp]),
     ("sgl_dev_solve", _i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _dbl, _dbl, _vp]),
+    ("sgl_dev_update_rhs", _i32, [_vp, _vp, _vp, _i32, C.POINTER(_u64)]),
+    ("sgl_dev_rhs_epoch", _u64, [_vp]),
+    ("sgl_dev_update_solve", _i32, [_vp, _vp, _u64, _vp, _i32, _vp, _dbl, _dbl, _vp]),
     ("sgl_dev_finish_d", _i32, [_vp, _i32, _vp]),
+    ("sgl_dev_finish_d_rescale_gram", _i32, [_vp, _i32, _vp, _vp]),
     ("sgl_dev_scale", _i32, [_vp, _vp, _i32, _i64, _vp]),
     ("sgl_dev_cor_sums", _i32, [_vp, _vp, _vp, _i32, _i64, _vp]),
     ("sgl_cor_from_sums", _dbl, [_vp, _dbl]),
@@ -120,6 +124,7 @@ SYMBOLS = [
     ("sgl_comm_collectives", _i64, [_vp]),
     ("sgl_fit_create", _i32, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _u64, _u64, C.POINTER(_vp)]),
     ("sgl_fit_iterate", _i32, [_vp, _dbl, _dbl, _dbl, _dbl, C.POINTER(_dbl), C.POINTER(_i32)]),
+    ("sgl_fit_set_lookahead", _i32, [_vp, _i32]),
     ("sgl_fit_test_mse", _i32, [_vp, C.POINTER(_dbl)]),
     ("sgl_fit_download", _i32, [_vp, _vp, _vp, _vp]),
     ("sgl_fit_shard", _i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),

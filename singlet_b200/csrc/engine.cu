@@ -110,6 +110,8 @@ struct sgl_handle {
     bool own_stream = false;
     int sm_count = 148;
     int64_t launches = 0;
+    uint64_t rhs_epoch = 0;  // bumped by every dev_rhs: who wrote `bparts` last (sgl_dev_update_rhs / sgl_dev_update_solve)
+    int upd_splits = 1;      // partial buffers the last dev_rhs left in `bparts`
     bool cache = true;
     DevBuf<float> bparts, blink, gram_f, gram_f_nojit, inv_diag;
     // FP16 shadow of the gather operand of the SpMM in flight (spmm_h16.cuh) + {max |F| bits, 2^-se}
@@ -880,6 +882,8 @@ static int dev_rhs(sgl_handle* h, const sgl_matrix* Xc, const sgl_mask* mask, co
         }
     }
     *splits_out = splits;
+    h->upd_splits = splits;
+    ++h->rhs_epoch;
     return SGL_OK;
 }
 
@@ -898,10 +902,13 @@ static ConstGramGuard& const_gram_guard(int device) {
 static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64_t* colptr, int64_t ncol, const sgl_mask* mask,
                      const float* F_in, float* F_out, int k, const double* gram, double L1, double L2, double* rowsum) {
     const int KPV = kp_of(k);
-    SGL_TRY(h->gram_f.ensure((size_t)KPV * KPV));
+    // float Gram and, behind it at the fixed offset the constant-memory image uses (nnls.cuh: c_gram), the reciprocal diagonal
+    const size_t inv_off = KPV <= 64 ? (size_t)64 * 64 : (size_t)KPV * KPV;
+    SGL_TRY(h->gram_f.ensure(inv_off + (size_t)(KPV <= 64 ? 64 : KPV)));
     SGL_TRY(h->gram_f_nojit.ensure((size_t)KPV * KPV));
-    SGL_TRY(h->inv_diag.ensure((size_t)KPV));
-    gram_finish_kernel<<<1, 256, 0, h->stream>>>(gram, k, KPV, h->gram_f.p, h->gram_f_nojit.p, h->inv_diag.p);
+    SGL_TRY(h->workctr.ensure(4));
+    float* const inv_diag = h->gram_f.p + inv_off;
+    gram_finish_kernel<<<1, 256, 0, h->stream>>>(gram, k, KPV, h->gram_f.p, h->gram_f_nojit.p, inv_diag, h->workctr.p);
     LAUNCH_CHECK(h);
     ProfScope ps_nnls(h, PK_NNLS, 0);
     int64_t n_parts = 0;
@@ -931,15 +938,14 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
                 cudaStreamSynchronize(h->stream);
                 if (st[3]) fprintf(stderr, "[nnls] previous launch: %llu columns, mean sweeps %.2f\n", st[3], (double)st[2] / (double)st[3]);
             }
-            SGL_CUDA(cudaMemsetAsync(h->workctr.p, 0, 4 * sizeof(unsigned long long), h->stream));
+            if (dbg_stats) SGL_CUDA(cudaMemsetAsync(h->workctr.p, 0, 4 * sizeof(unsigned long long), h->stream));  // else: zeroed by gram_finish_kernel
             // Gram + reciprocal diagonal -> constant memory (uniform-datapath operands of the solver). The symbols are
             // per device, not per handle: handles on other streams of this device are held back (stream-ordered, no host
             // wait) until the solver that reads the current contents has finished, and the host section is under a mutex.
             ConstGramGuard& cg = const_gram_guard(h->device);
             std::lock_guard<std::mutex> cg_lock(cg.mu);
             if (cg.ev && cg.last_stream != h->stream) SGL_CUDA(cudaStreamWaitEvent(h->stream, cg.ev, 0));
-            SGL_CUDA(cudaMemcpyToSymbolAsync(c_gram, h->gram_f.p, sizeof(float) * KPV * KPV, 0, cudaMemcpyDeviceToDevice, h->stream));
-            SGL_CUDA(cudaMemcpyToSymbolAsync(c_inv_diag, h->inv_diag.p, sizeof(float) * KPV, 0, cudaMemcpyDeviceToDevice, h->stream));
+            SGL_CUDA(cudaMemcpyToSymbolAsync(c_gram, h->gram_f.p, sizeof(float) * (64 * 64 + 64), 0, cudaMemcpyDeviceToDevice, h->stream));
             switch (KPV) {
 #define NNLS_LAUNCH(KPC, NTC, NCLC, ...)                                                                             \
     {                                                                                                               \
@@ -1014,7 +1020,7 @@ static int dev_solve(sgl_handle* h, const float* Bparts, int splits, const int64
             n_parts = (ncol + 31) / 32;
             SGL_TRY(h->part.ensure((size_t)n_parts * KPV));
             const size_t smem = 2 * (size_t)KPV * 32 * sizeof(float);
-            nnls_cols_big_kernel<<<(unsigned)n_parts, 32, smem, h->stream>>>(Bparts, splits, F_out, h->gram_f.p, h->inv_diag.p,
+            nnls_cols_big_kernel<<<(unsigned)n_parts, 32, smem, h->stream>>>(Bparts, splits, F_out, h->gram_f.p, inv_diag,
                                                                             colptr, ncol, k, KPV, (float)L1, (float)L2, h->part.p);
         }
         LAUNCH_CHECK(h);
@@ -2376,6 +2382,38 @@ int sgl_dev_update(sgl_handle* h, const sgl_matrix* X, const float* F_in, float*
     SGL_TRY(check_k(k));
     SGL_TRY(set_device(h));
     return dev_update(h, X, nullptr, F_in, F_out, k, gram, L1, L2, rowsum);
+}
+int sgl_dev_update_rhs(sgl_handle* h, const sgl_matrix* X, const float* F_in, int k, uint64_t* epoch_out) {
+    if (!h || !X || !F_in || !epoch_out) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    if (X->ncol > 0) {
+        int splits = 1;
+        SGL_TRY(dev_rhs(h, X, nullptr, F_in, k, &splits));
+    }
+    *epoch_out = h->rhs_epoch;
+    return SGL_OK;
+}
+uint64_t sgl_dev_rhs_epoch(const sgl_handle* h) { return h ? h->rhs_epoch : 0; }
+int sgl_dev_update_solve(sgl_handle* h, const sgl_matrix* X, uint64_t epoch, float* F_out, int k, const double* gram, double L1,
+                         double L2, double* rowsum) {
+    if (!h || !X || !F_out || !gram || !rowsum) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    if (X->ncol == 0) {
+        SGL_CUDA(cudaMemsetAsync(rowsum, 0, sizeof(double) * kp_of(k), h->stream));
+        return SGL_OK;
+    }
+    if (epoch != h->rhs_epoch) return fail(SGL_EINVAL, "sgl_dev_update_solve: the handle's right-hand sides were overwritten since sgl_dev_update_rhs");
+    return dev_solve(h, h->bparts.p, h->upd_splits, X->colptr, X->ncol, nullptr, nullptr, F_out, k, gram, L1, L2, rowsum);
+}
+int sgl_dev_finish_d_rescale_gram(sgl_handle* h, int k, double* d, double* gram) {
+    if (!h || !d || !gram) return fail(SGL_EINVAL, "NULL argument");
+    SGL_TRY(check_k(k));
+    SGL_TRY(set_device(h));
+    finish_d_rescale_gram_kernel<<<1, 256, 0, h->stream>>>(d, gram, k, kp_of(k));
+    LAUNCH_CHECK(h);
+    return SGL_OK;
 }
 int sgl_dev_rhs(sgl_handle* h, const sgl_matrix* X, const float* F_in, int k, float* B_out) {
     if (!h || !X || !F_in || !B_out) return fail(SGL_EINVAL, "NULL argument");

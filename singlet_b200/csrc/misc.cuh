@@ -78,7 +78,9 @@ gram_partial_kernel(const float* __restrict__ X, int64_t cols, double* __restric
 
 // gram (double, with jitter) -> float copy without the jitter on padding, reciprocal diagonal
 __global__ void gram_finish_kernel(const double* __restrict__ gram, int k, int KP, float* __restrict__ gram_f,
-                                   float* __restrict__ gram_f_nojit, float* __restrict__ inv_diag) {
+                                   float* __restrict__ gram_f_nojit, float* __restrict__ inv_diag,
+                                   unsigned long long* __restrict__ zero4 /* work counters of the solver that follows, or NULL */) {
+    if (zero4 && threadIdx.x < 4) zero4[threadIdx.x] = 0ull;
     for (int t = threadIdx.x; t < KP * KP; t += blockDim.x) {
         const int r = t / KP, c = t % KP;
         const double g = gram[t];
@@ -94,6 +96,24 @@ __global__ void add_jitter_kernel(double* gram, int k, int KP) {
 __global__ void finish_d_kernel(double* d, int k, int KP) {
     const int r = threadIdx.x;
     if (r < KP) d[r] = (r < k) ? d[r] + 1e-15 : 1.0;
+}
+// finish_d, then the Gram of the UNSCALED factor becomes the Gram of the scaled one, G[i][j] / (d[i] d[j]), plus the
+// jitter (src/singlet.cpp:206): lets the sharded driver all-reduce the row sums and the partial Grams in one collective
+__global__ void finish_d_rescale_gram_kernel(double* d, double* gram, int k, int KP) {
+    __shared__ double sd[128];
+    for (int r = threadIdx.x; r < KP; r += blockDim.x) {
+        const double v = (r < k) ? d[r] + 1e-15 : 1.0;
+        d[r] = v;
+        sd[r] = v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < KP * KP; t += blockDim.x) {
+        const int r = t / KP, c = t % KP;
+        if (r < k && c < k) {
+            const double g = gram[t] / (sd[r] * sd[c]);
+            gram[t] = (r == c) ? g + 1e-15 : g;
+        }
+    }
 }
 
 // scale (src/singlet.cpp:222-224): X[c][f] /= d[f]

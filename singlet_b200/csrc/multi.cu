@@ -136,13 +136,13 @@ struct sgl_comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, device = 0;
     cudaStream_t stream = nullptr;
-    double* pinned = nullptr;  // 64 doubles
+    double* pinned = nullptr;  // 256 doubles (d of up to SGL_MAX_RANK factors is read back through it)
     int64_t collectives = 0;
 };
 
 static int comm_finish(sgl_comm* c) {
     c->stream = (cudaStream_t)sgl_stream(c->h);
-    if (cudaMallocHost(&c->pinned, sizeof(double) * 64) != cudaSuccess) return fail(SGL_ENOMEM, "cudaMallocHost failed");
+    if (cudaMallocHost(&c->pinned, sizeof(double) * 256) != cudaSuccess) return fail(SGL_ENOMEM, "cudaMallocHost failed");
     return SGL_OK;
 }
 
@@ -248,6 +248,11 @@ struct sgl_fit {
     double *gram = nullptr, *dvec = nullptr, *sums = nullptr;
     int64_t* gene_ptr = nullptr;     // plain: int64[m + 1], equal consecutive entries where a gene is empty in the GLOBAL matrix
     int64_t iterations = 0;
+    // plain fits: the part of the next iteration that only READS W (Wprev <- W, Gram of W, right-hand sides of the H update) is
+    // enqueued before the host waits for this iteration's tol, so the device never idles across the host round trip
+    bool lookahead = true, head_ready = false, flag_slot_dirty = false;
+    uint64_t head_ticket = 0;
+    cudaEvent_t ev_done = nullptr;
 };
 
 static void fit_release(sgl_fit* f) {
@@ -257,7 +262,8 @@ static void fit_release(sgl_fit* f) {
     if (f->mAt) sgl_mask_free(f->c->h, f->mAt);
     if (f->At_own) sgl_matrix_free(f->c->h, f->At_own);
     cudaFree(f->W); cudaFree(f->Wprev); cudaFree(f->H); cudaFree(f->Bw);
-    cudaFree(f->gram); cudaFree(f->dvec); cudaFree(f->sums); cudaFree(f->gene_ptr);
+    cudaFree(f->gram); cudaFree(f->gene_ptr);  // dvec and sums live behind gram
+    if (f->ev_done) cudaEventDestroy(f->ev_done);
     delete f;
 }
 
@@ -321,9 +327,11 @@ extern "C" int sgl_fit_create(sgl_comm* c, const sgl_matrix* A_loc, const sgl_ma
         alloc((void**)&f->Wprev, sizeof(float) * w_rows * KP);
         alloc((void**)&f->H, sizeof(float) * h_rows * KP);
         if (!f->masked) alloc((void**)&f->Bw, sizeof(float) * w_rows * KP);
-        alloc((void**)&f->gram, sizeof(double) * KP * KP);
-        alloc((void**)&f->dvec, sizeof(double) * (KP + 8));
-        alloc((void**)&f->sums, sizeof(double) * 8);
+        // [Gram KP x KP | d KP | stop flag | pad]: one buffer, so that the partial Gram, the row sums and the flag of the
+        // H update travel in ONE all-reduce
+        alloc((void**)&f->gram, sizeof(double) * (KP * KP + KP + 8));
+        if (e == cudaSuccess) f->dvec = f->gram + (size_t)KP * KP;
+        if (e == cudaSuccess) f->sums = f->dvec + KP + 1;  // [flag | 5 sums of cor | loss]: one read-back per iteration
         if (!f->masked) alloc((void**)&f->gene_ptr, sizeof(int64_t) * (w_rows + 2));
         if (e != cudaSuccess) { rc = fail(SGL_ENOMEM, "sgl_fit_create: cudaMalloc failed: %s", cudaGetErrorString(e)); break; }
         if ((rc = sgl_factor_upload(c->h, w_init, k, m, f->W)) != SGL_OK) break;  // every rank holds the full w_init
@@ -357,8 +365,33 @@ extern "C" int sgl_fit_create(sgl_comm* c, const sgl_matrix* A_loc, const sgl_ma
     return SGL_OK;
 }
 
-// One ALS iteration. stop_flag (optional, in/out): every rank passes 0 or 1; the values are summed with the row sums of the
-// W update, so all ranks leave with the same non-zero value when ANY rank asked to stop (interrupts in a one-process job).
+// The head of a plain iteration: everything that only READS the replicated W -- Wprev <- W, the Gram of W (no collective: W is
+// replicated) and the right-hand sides of the H update, left in the handle's scratch under a ticket.
+static int plain_head(sgl_fit* f) {
+    sgl_comm* c = f->c;
+    sgl_handle* h = c->h;
+    const size_t w_rows = (size_t)f->g_per * c->world;
+    SGL_CUDA(cudaMemcpyAsync(f->Wprev, f->W, sizeof(float) * w_rows * f->KP, cudaMemcpyDeviceToDevice, c->stream));
+    SGL_TRY(sgl_dev_gram(h, f->W, f->k, f->m, f->gram, 1));
+    SGL_TRY(sgl_dev_update_rhs(h, f->A, f->W, f->k, &f->head_ticket));
+    f->head_ready = true;
+    return SGL_OK;
+}
+
+extern "C" int sgl_fit_set_lookahead(sgl_fit* f, int on) {
+    if (!f) return fail(SGL_EINVAL, "NULL fit");
+    f->lookahead = on != 0;
+    return SGL_OK;
+}
+
+// One ALS iteration. stop_flag (optional, in/out): every rank passes 0 or 1; the values are summed in an all-reduce the
+// iteration makes anyway, so all ranks leave with the same non-zero value when ANY rank asked to stop (interrupts in a
+// one-process job).
+// Collectives of a plain iteration on more than one rank: ONE all-reduce of [partial Gram of the unscaled H | row sums of H |
+// stop flag] (the Gram is rescaled by 1 / (d_i d_j) afterwards, sgl_dev_finish_d_rescale_gram), the reduce-scatter of the
+// W-update right-hand sides, and ONE grouped launch of {all-reduce of the W row sums, all-gather of the unscaled W shard};
+// every rank then scales the whole W by the same d. SGL_FIT_COLLECTIVES=split restores the five separate collectives of
+// the first version (A/B runs).
 extern "C" int sgl_fit_iterate(sgl_fit* f, double L1_w, double L1_h, double L2_w, double L2_h, double* tol_out, int* stop_flag) {
     if (!f) return fail(SGL_EINVAL, "NULL fit");
     sgl_comm* c = f->c;
@@ -367,24 +400,38 @@ extern "C" int sgl_fit_iterate(sgl_fit* f, double L1_w, double L1_h, double L2_w
     const int64_t m = f->m, n_loc = f->c1 - f->c0, g_loc = f->g1 - f->g0;
     SGL_CUDA(cudaSetDevice(c->device));
     const size_t w_rows = (size_t)f->g_per * c->world;
-    SGL_CUDA(cudaMemcpyAsync(f->Wprev, f->W, sizeof(float) * w_rows * KP, cudaMemcpyDeviceToDevice, c->stream));
     float* H_loc = f->masked ? f->H + (size_t)f->c0 * KP : f->H;
     float* W_loc = f->W + (size_t)f->g0 * KP;
+    static const bool split_env = [] { const char* e = getenv("SGL_FIT_COLLECTIVES"); return e && strcmp(e, "split") == 0; }();
+    const bool merged = !f->masked && c->world > 1 && !split_env;
+    const double flag = (stop_flag && *stop_flag) ? 1.0 : 0.0;
+    c->pinned[40] = flag;
     if (!f->masked) {
-        // ---- H update over the local cells against the replicated W (its Gram needs no collective) ----
-        SGL_TRY(sgl_dev_gram(h, f->W, k, m, f->gram, 1));
-        SGL_TRY(sgl_dev_update(h, f->A, f->W, H_loc, k, f->gram, L1_h, L2_h, f->dvec));
-        SGL_TRY(all_reduce_f64(c, f->dvec, (size_t)KP));
-        SGL_TRY(sgl_dev_finish_d(h, k, f->dvec));
-        SGL_TRY(sgl_dev_scale(h, H_loc, k, n_loc, f->dvec));
-        // ---- W update: partial Gram and partial right-hand sides of ALL genes from the local cells ----
-        SGL_TRY(sgl_dev_gram(h, H_loc, k, n_loc, f->gram, 0));
-        SGL_TRY(all_reduce_f64(c, f->gram, (size_t)KP * KP));
-        SGL_TRY(sgl_dev_gram_jitter(h, k, f->gram));
+        if (!(f->head_ready && f->head_ticket == sgl_dev_rhs_epoch(h))) SGL_TRY(plain_head(f));
+        f->head_ready = false;
+        // ---- H update over the local cells against the replicated W ----
+        SGL_TRY(sgl_dev_update_solve(h, f->A, f->head_ticket, H_loc, k, f->gram, L1_h, L2_h, f->dvec));
+        if (merged) {
+            SGL_TRY(sgl_dev_gram(h, H_loc, k, n_loc, f->gram, 0));  // of the UNSCALED H
+            if (flag != 0.0 || f->flag_slot_dirty)                  // the slot holds 0 otherwise
+                SGL_CUDA(cudaMemcpyAsync(f->dvec + KP, c->pinned + 40, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            SGL_TRY(all_reduce_f64(c, f->gram, (size_t)KP * KP + KP + 1));
+            SGL_TRY(sgl_dev_finish_d_rescale_gram(h, k, f->dvec, f->gram));
+            SGL_TRY(sgl_dev_scale(h, H_loc, k, n_loc, f->dvec));
+        } else {
+            SGL_TRY(all_reduce_f64(c, f->dvec, (size_t)KP));
+            SGL_TRY(sgl_dev_finish_d(h, k, f->dvec));
+            SGL_TRY(sgl_dev_scale(h, H_loc, k, n_loc, f->dvec));
+            SGL_TRY(sgl_dev_gram(h, H_loc, k, n_loc, f->gram, 0));
+            SGL_TRY(all_reduce_f64(c, f->gram, (size_t)KP * KP));
+            SGL_TRY(sgl_dev_gram_jitter(h, k, f->gram));
+        }
+        // ---- W update: partial right-hand sides of ALL genes from the local cells, summed onto the gene shards ----
         SGL_TRY(sgl_dev_rhs(h, f->At, H_loc, k, f->Bw));
         SGL_TRY(reduce_scatter_rows(c, f->Bw, f->g_per, KP));
         SGL_TRY(sgl_dev_solve(h, f->Bw + (size_t)f->g0 * KP, f->gene_ptr + f->g0, g_loc, W_loc, k, f->gram, L1_w, L2_w, f->dvec));
     } else {
+        SGL_CUDA(cudaMemcpyAsync(f->Wprev, f->W, sizeof(float) * w_rows * KP, cudaMemcpyDeviceToDevice, c->stream));
         // ---- H update: Gram of W summed over the ranks' gene shards; masked solve of the local cells; H all-gathered ----
         SGL_TRY(sgl_dev_gram(h, W_loc, k, g_loc, f->gram, 0));
         SGL_TRY(all_reduce_f64(c, f->gram, (size_t)KP * KP));
@@ -400,20 +447,39 @@ extern "C" int sgl_fit_iterate(sgl_fit* f, double L1_w, double L1_h, double L2_w
         SGL_TRY(sgl_dev_gram_jitter(h, k, f->gram));
         SGL_TRY(sgl_dev_update_masked(h, f->At, f->mAt, f->H, W_loc, k, f->gram, L1_w, L2_w, f->dvec));
     }
-    // row sums of the W update (+ the stop flag of every rank in the spare slot behind them)
-    const double flag = (stop_flag && *stop_flag) ? 1.0 : 0.0;
-    c->pinned[40] = flag;
-    SGL_CUDA(cudaMemcpyAsync(f->dvec + KP, c->pinned + 40, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    SGL_TRY(all_reduce_f64(c, f->dvec, (size_t)KP + 1));
-    SGL_TRY(sgl_dev_finish_d(h, k, f->dvec));
-    SGL_TRY(sgl_dev_scale(h, W_loc, k, g_loc, f->dvec));
-    SGL_TRY(all_gather_rows(c, f->W, f->g_per, KP));
+    if (merged) {
+        // row sums of the W update and the unscaled shards in one NCCL launch; every rank scales the whole W by the same d
+        NcclApi* api = nccl_api();
+        SGL_NCCL(api, api->GroupStart());
+        int rc_a = all_reduce_f64(c, f->dvec, (size_t)KP);
+        int rc_b = rc_a == SGL_OK ? all_gather_rows(c, f->W, f->g_per, KP) : rc_a;
+        SGL_NCCL(api, api->GroupEnd());
+        if (rc_b != SGL_OK) return rc_b;
+        SGL_TRY(sgl_dev_finish_d(h, k, f->dvec));
+        SGL_TRY(sgl_dev_scale(h, f->W, k, m, f->dvec));
+    } else {
+        // row sums of the W update (+ the stop flag of every rank in the spare slot behind them)
+        SGL_CUDA(cudaMemcpyAsync(f->dvec + KP, c->pinned + 40, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        SGL_TRY(all_reduce_f64(c, f->dvec, (size_t)KP + 1));
+        SGL_TRY(sgl_dev_finish_d(h, k, f->dvec));
+        SGL_TRY(sgl_dev_scale(h, W_loc, k, g_loc, f->dvec));
+        SGL_TRY(all_gather_rows(c, f->W, f->g_per, KP));
+    }
     SGL_TRY(sgl_dev_cor_sums(h, f->W, f->Wprev, k, m, f->sums));  // replicated W: the same value on every rank
-    SGL_CUDA(cudaMemcpyAsync(c->pinned, f->sums, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->stream));
-    SGL_CUDA(cudaMemcpyAsync(c->pinned + 41, f->dvec + KP, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    SGL_CUDA(cudaStreamSynchronize(c->stream));
-    if (tol_out) *tol_out = sgl_cor_from_sums(c->pinned, (double)k * (double)m);
-    if (stop_flag) *stop_flag = c->pinned[41] > 0.5 ? 1 : 0;
+    SGL_CUDA(cudaMemcpyAsync(c->pinned + 41, f->dvec + KP, sizeof(double) * 6, cudaMemcpyDeviceToHost, c->stream));  // flag, 5 sums
+    if (!f->masked && f->lookahead) {
+        // the host waits for this iteration's numbers only; the head of the next one is already queued behind them
+        if (!f->ev_done) SGL_CUDA(cudaEventCreateWithFlags(&f->ev_done, cudaEventDisableTiming));
+        SGL_CUDA(cudaEventRecord(f->ev_done, c->stream));
+        SGL_TRY(plain_head(f));
+        SGL_CUDA(cudaEventSynchronize(f->ev_done));
+    } else {
+        SGL_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (tol_out) *tol_out = sgl_cor_from_sums(c->pinned + 42, (double)k * (double)m);
+    const bool stopped = c->pinned[41] > 0.5;
+    f->flag_slot_dirty = stopped;
+    if (stop_flag) *stop_flag = stopped ? 1 : 0;
     ++f->iterations;
     return SGL_OK;
 }
@@ -487,6 +553,7 @@ static int nmf_rank(sgl_comm* c, const sgl_matrix* A_loc, const sgl_matrix* At_l
         int stop = 0;
         if (cb && cb->poll_interrupt && cb->poll_interrupt(cb->user)) stop = 1;
         if (shared && shared->stop.load()) stop = 1;
+        f->lookahead = (int)iter_ + 1 < (int)maxit;  // no product for an iteration that will not run
         if ((rc = sgl_fit_iterate(f, L1_w, L1_h, L2_w, L2_h, &tol_, &stop)) != SGL_OK) break;
         if (cb && cb->on_iter) cb->on_iter(cb->user, iter_ + 1, tol_, NAN);
         if (shared && c->rank == 0) {

@@ -84,8 +84,9 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
 // of the plain solver reads the same a[i][j] at the same time, so the loads go through the uniform
 // datapath (LDCU -> uniform registers feeding FFMA2 directly) and never touch the shared-memory
 // crossbar or the vector register file. Refreshed by cudaMemcpyToSymbolAsync before each launch.
-__constant__ __align__(16) float c_gram[64 * 64];
-__constant__ float c_inv_diag[64];
+// One symbol, one copy per solve: the Gram in the first 64 x 64 floats, the reciprocal diagonal behind it.
+__constant__ __align__(16) float c_gram[64 * 64 + 64];
+#define c_inv_diag (c_gram + 64 * 64)
 
 // Persistent kernel with lane refill. Every lane solves NCL = 2 columns at a time (two independent
 // dependency chains per thread, and every Gram row fetched once feeds both). Columns converge after
