@@ -18,7 +18,8 @@ W-update right-hand sides from its local H shard, and the k x m partials are red
 that every rank solves one gene shard; W (3.84 MB at the headline config) is then all-gathered.
 H is never gathered (128 MB per iteration saved) and the W-update SpMM keeps all m gene columns per
 rank, which fills the SMs much better than a 1/N gene shard. Masked (CV) fits stay on layout "A"
-because the per-gene Gram corrections would otherwise need a k^2 x m all-reduce.
+because the per-gene Gram corrections would otherwise need a k^2 x m all-reduce. Layout "B3" is layout B with three
+exchanges per iteration instead of five -- the scheme csrc/multi.cu uses on more than one rank (``iteration_b3``).
 
 ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the plumbing; the compute calls go to
 a *backend*: :class:`CudaBackend` (the C ABI device layer) in production. The CPU tests inject their
@@ -173,6 +174,9 @@ class CudaBackend:
     def scale(self, F, k, cols, d):
         _lib.check(self.lib.sgl_dev_scale(self._h, F.data_ptr(), k, cols, d.data_ptr()))
 
+    def finish_d_rescale_gram(self, k, d, gram):
+        _lib.check(self.lib.sgl_dev_finish_d_rescale_gram(self._h, k, d.data_ptr(), gram.data_ptr()))
+
     def cor_sums(self, X, Y, k, cols, out):
         _lib.check(self.lib.sgl_dev_cor_sums(self._h, X.data_ptr(), Y.data_ptr(), k, cols, out.data_ptr()))
 
@@ -221,11 +225,11 @@ class ShardedNMF:
         self.be, self.m, self.n, self.k = backend, m, n, k
         self.rank, self.world, self.group = rank, world, group
         self.layout = layout
-        if layout == "B" and (mask_A is not None or mask_At is not None):
+        if layout in ("B", "B3") and (mask_A is not None or mask_At is not None):
             raise ValueError("layout B does not support the masked (CV) solve")
         if At_shard is None:
             # layout B: the transpose of the local cell block is built on the device (row f1), so a rank uploads only A
-            if layout != "B" and world > 1:
+            if layout not in ("B", "B3") and world > 1:
                 raise ValueError("layout A needs the gene block over all cells; only layout B can derive At_shard from A_shard")
             At_shard = backend.transpose(A_shard)
         self.A, self.At, self.mask_A, self.mask_At = A_shard, At_shard, mask_A, mask_At
@@ -238,11 +242,13 @@ class ShardedNMF:
         self.Wprev = be.zeros_factor(self.g_per * world, k)
         kp = be.kp(k)
         self.kp = kp
-        self.gram = be.zeros_f64(kp * kp)
-        self.d = be.zeros_f64(kp)
+        # [Gram | d | spare]: one buffer, so that layout "B3" sends the partial Gram and the row sums in ONE all-reduce
+        self.red = be.zeros_f64(kp * kp + kp + 1)
+        self.gram = self.red[:kp * kp]
+        self.d = self.red[kp * kp:kp * kp + kp]
         self.sums = be.zeros_f64(8)
         self.n_collectives = 0
-        if layout == "B":
+        if layout in ("B", "B3"):
             # right-hand sides of all m genes (padded to g_per * world rows for the reduce-scatter) and the
             # global "gene has any non-zero" test (src/singlet.cpp:340 skips empty columns)
             self.Bw = be.zeros_factor(self.g_per * world, k)
@@ -324,6 +330,34 @@ class ShardedNMF:
         s = self.sums[:5].cpu().numpy()
         return be.cor_from_sums(s, float(k) * float(self.m))
 
+    def iteration_b3(self, L1_w, L1_h, L2_w, L2_h):
+        """Layout B with THREE exchanges per iteration instead of five -- the scheme of csrc/multi.cu sgl_fit_iterate on more
+        than one rank: the partial Gram of the UNSCALED H and the row sums of H travel in one all-reduce and the Gram is
+        rescaled afterwards (G_ij / (d_i d_j), sgl_dev_finish_d_rescale_gram); the W row sums are reduced next to the
+        all-gather of the UNSCALED W shard (one grouped NCCL launch in the library) and every rank scales the whole W."""
+        be, k, kp = self.be, self.k, self.kp
+        self.Wprev.copy_(self.W)
+        be.gram(self.W, k, self.m, self.gram, jitter=True)
+        h_local = self.H[self.c0:self.c0 + self.c_per]
+        be.update(self.A, None, self.W, h_local, k, self.gram, L1_h, L2_h, self.d)   # d <- local row sums of H
+        be.gram(h_local, k, self.c1 - self.c0, self.gram, jitter=False)               # of the unscaled H
+        self._allreduce(self.red[:kp * kp + kp])
+        be.finish_d_rescale_gram(k, self.d, self.gram)
+        be.scale(h_local, k, self.c1 - self.c0, self.d)
+        be.rhs(self.At, h_local, k, self.Bw)
+        self._reduce_scatter_rows(self.Bw, self.g_per)
+        w_local = self.W[self.g0:self.g0 + self.g_per]
+        be.solve(self.Bw[self.g0:self.g0 + self.g_per], self.gene_ptr[self.g0:self.g0 + self.g_per + 1] if self.g1 > self.g0
+                 else self.gene_ptr[0:1], self.g1 - self.g0, w_local, k, self.gram, L1_w, L2_w, self.d)
+        self._allreduce(self.d)                    # grouped with the all-gather in the library: one launch
+        self._allgather_rows(self.W, self.g_per)   # unscaled shards
+        self.n_collectives -= 1 if self.world > 1 else 0
+        be.finish_d(k, self.d)
+        be.scale(self.W, k, self.m, self.d)        # every rank: the whole W by the same d
+        be.cor_sums(self.W, self.Wprev, k, self.m, self.sums)
+        s = self.sums[:5].cpu().numpy()
+        return be.cor_from_sums(s, float(k) * float(self.m))
+
     def gather_h(self):
         """Layout B keeps H sharded; gather it once (e.g. for the final output)."""
         self._allgather_rows(self.H, self.c_per)
@@ -332,6 +366,8 @@ class ShardedNMF:
         """One trip of src/singlet.cpp:648-659. Returns tol (1 - cor) as a python float (synchronises)."""
         if self.layout == "B":
             return self.iteration_b(L1_w, L1_h, L2_w, L2_h)
+        if self.layout == "B3":
+            return self.iteration_b3(L1_w, L1_h, L2_w, L2_h)
         be, k = self.be, self.k
         self.Wprev.copy_(self.W)
         # H update over local cells; Gram of W: each rank sums its own genes
@@ -352,7 +388,7 @@ class ShardedNMF:
         return float(out.cpu().numpy()[0]) / float(self.n)
 
     def factors_to_host(self):
-        if self.layout == "B":
+        if self.layout in ("B", "B3"):
             self.gather_h()
         w = self.be.factor_to_host(self.W, self.k, self.m)
         h = self.be.factor_to_host(self.H, self.k, self.n)

@@ -123,6 +123,13 @@ class OracleBackend:
     def scale(self, F, k, cols, d):
         F[:cols, :k] /= d[:k]
 
+    def finish_d_rescale_gram(self, k, d, gram):
+        kp = self.kp(k)
+        self.finish_d(k, d)
+        g = gram.view(kp, kp)
+        g[:k, :k] /= torch.outer(d[:k], d[:k])
+        self.gram_jitter(k, gram)
+
     def cor_sums(self, X, Y, k, cols, out):
         x, y = X[:cols, :k].numpy().ravel(), Y[:cols, :k].numpy().ravel()
         out[:5] = torch.tensor([x.sum(), y.sum(), (x * y).sum(), (x * x).sum(), (y * y).sum()], dtype=torch.float64)
@@ -148,7 +155,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from singlet_b200 import synth
+        from singlet_b200 import sharded, synth
         from singlet_b200.sharded import shard_bounds, sharded_ard_nmf, sharded_nmf
 
         m, n, k = 41, 37, 3  # ragged on purpose: neither divides by 2
@@ -166,7 +173,14 @@ def _worker(rank, world, port, q):
         # (rank 0 hands it over, rank 1 lets the driver derive it from its cell block: At_shard = None)
         resb = sharded_nmf(be, m, n, k, A[:, c0:c1].tocsc(), A[:, c0:c1].T.tocsc() if rank == 0 else None, w0, tol=0.0, maxit=4,
                            L1=(0.01, 0.02), rank=rank, world=world, layout="B")
-        q.put((rank, res["w"], res["h"], res["d"], res["tol"], cv["test_mse"], cv["h"], resb["w"], resb["h"], resb["d"]))
+        # layout B with three exchanges per iteration (the scheme of csrc/multi.cu on more than one rank)
+        fit3 = sharded.ShardedNMF(be, m, n, k, A[:, c0:c1].tocsc(), None, rank, world, None, layout="B3")
+        fit3.set_w(w0)
+        tol3 = [fit3.iteration(0.01, 0.02, 0.0, 0.0) for _ in range(4)]
+        per_iter = fit3.n_collectives / 4
+        w3, d3, h3 = fit3.factors_to_host()
+        q.put((rank, res["w"], res["h"], res["d"], res["tol"], cv["test_mse"], cv["h"], resb["w"], resb["h"], resb["d"],
+               w3, h3, d3, tol3[-1], per_iter))
     finally:
         dist.destroy_process_group()
 
@@ -190,7 +204,11 @@ def test_two_rank_gloo_matches_unsharded_oracle(oracle):
     w0 = synth.w_init(k, m, seed=2)
     ref = oracle.nmf(A, At, w0, tol=0.0, maxit=4, L1=(0.01, 0.02))
     cvr = oracle.ard_nmf(A, At, w0, 123, 5, tol=0.0, maxit=3, overfit_threshold=10.0, trace_test_mse=2)
-    for rank, w, h, d, tol, mse, hcv, wb, hb, db in outs:  # every rank ends with the full replicated model
+    for rank, w, h, d, tol, mse, hcv, wb, hb, db, w3, h3, d3, tol3, per_iter in outs:  # every rank ends with the full replicated model
+        # three exchanges per iteration (+ the one-off all-reduce of the gene counts at construction, 1/4 per iteration here): same fit
+        assert per_iter == 3.25
+        assert np.allclose(w3, ref["w"], rtol=1e-9, atol=1e-12) and np.allclose(h3, ref["h"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(d3, ref["d"], rtol=1e-9) and abs(tol3 - ref["tol"][-1]) < 1e-9
         assert np.allclose(w, ref["w"], rtol=1e-9, atol=1e-12) and np.allclose(h, ref["h"], rtol=1e-9, atol=1e-12)
         assert np.allclose(d, ref["d"], rtol=1e-9) and abs(tol - ref["tol"][-1]) < 1e-9
         assert np.allclose(mse, cvr["test_mse"], rtol=1e-9) and np.allclose(hcv, cvr["h"], rtol=1e-8, atol=1e-12)
