@@ -362,6 +362,8 @@ def main():
                "roofline": {"bound": "hbm", "kernel": kernel + " (mean of the H-update and W-update launches, rank 0)",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": ncu_traffic(args.config, world, kernel),
+                            "traffic_source": "profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from the "
+                                              "committed ncu --set full capture of this command (null when this configuration was not captured)",
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes,
                             "ms_per_launch": per_launch_ms, "launches_timed": spmm_cnt},
                "breakdown_ms_per_step_rank0": {"spmm": spmm_ms / args.steps, "nnls": prof["nnls"][0] / args.steps,
