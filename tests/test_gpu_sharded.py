@@ -27,6 +27,12 @@ def test_sharded_driver_world1_matches_c_driver(oracle):
         assert np.array_equal(sb["w"], c["w"]) and np.array_equal(sb["h"], c["h"])
         sn = sharded_nmf(be, m, n, k, hA, None, w0, tol=0.0, maxit=6, L1=(0.01, 0.01), layout="B")  # transpose built on the device
         assert np.array_equal(sn["w"], c["w"]) and np.array_equal(sn["h"], c["h"])
+        # layout B3 = the three-exchange iteration of csrc/multi.cu: the Gram of H is the Gram of the unscaled H divided by
+        # d_i d_j (sgl_dev_finish_d_rescale_gram) instead of the Gram of the rounded scaled floats -- a rounding-level difference
+        s3 = sharded_nmf(be, m, n, k, hA, None, w0, tol=0.0, maxit=6, L1=(0.01, 0.01), layout="B3")
+        for nm in ("w", "h"):
+            assert np.abs(s3[nm] - c[nm]).max() <= 2e-4 * np.abs(c[nm]).max(), nm
+        assert np.allclose(s3["d"], c["d"], rtol=1e-5)
         sm = sharded_ard_nmf(be, m, n, k, hA, hAt, w0, 123, 20, tol=0.0, maxit=5, overfit_threshold=10.0, trace_test_mse=2)
         cm = api.c_ard_nmf(A, At, 0.0, 5, False, 0.01, 0, 0, w0, 123, 20, 10.0, 2)
         assert np.array_equal(sm["iter"], cm["iter"]) and np.allclose(sm["test_mse"], cm["test_mse"], rtol=1e-12)
